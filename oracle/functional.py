@@ -1,0 +1,435 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY -- never imported by the product path.
+
+Functional (stateless, dict-of-tensors) CPU restatement of the reference's segmentation hot path in plain
+PyTorch fp32.  It travels to the GPU box (where /root/reference does not exist) and is the checker for the CUDA
+path and the ``cpu_baseline`` / ``--impl reference`` leg of bench.py ("kind": "port").
+
+Pinned (tests/test_oracle.py) against the reference's own modules executed verbatim in the build container
+(oracle/refload.py) and against the committed tests/golden/*.pt those modules produced.
+
+Every function cites the reference lines it follows.  ``P`` is a flat ``{state_dict_key: tensor}`` mapping using the
+reference's checkpoint key names; BN running statistics in ``P`` are updated in place in training mode
+exactly as nn.BatchNorm2d does.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------------------------
+# elementary blocks
+# --------------------------------------------------------------------------------------------------------------
+
+
+def _bn(P, k, x, training, momentum=0.1, eps=1e-5):
+    """nn.BatchNorm2d semantics (train: batch stats + running update; eval: running stats)."""
+    if training and (k + ".num_batches_tracked") in P:
+        P[k + ".num_batches_tracked"] += 1
+    return F.batch_norm(x, P[k + ".running_mean"], P[k + ".running_var"], P[k + ".weight"], P[k + ".bias"],
+                        training, momentum, eps)
+
+
+def conv_layer(P, k, x, training):
+    """ConvLayer: 3x3 p1 no-bias conv -> BN -> LeakyReLU(0.01).  layers.py:89-100"""
+    y = F.conv2d(x, P[k + ".conv.weight"], None, 1, 1)
+    return F.leaky_relu(_bn(P, k + ".batch_norm", y, training), 0.01)
+
+
+def conv_block(P, k, x, training):
+    """ConvBlock = two ConvLayers.  layers.py:119-128"""
+    return conv_layer(P, k + ".conv2", conv_layer(P, k + ".conv1", x, training), training)
+
+
+def attention_layer(P, k, x, training):
+    """AttentionLayer: 1x1 no-bias conv -> BN.  layers.py:68-77"""
+    return _bn(P, k + ".batch_norm", F.conv2d(x, P[k + ".conv.weight"]), training)
+
+
+def upsample_block(P, k, x, skip, training, attention):
+    """UpsampleBlock (transposed-conv flavour).  layers.py:152-168"""
+    out = F.conv_transpose2d(x, P[k + ".conv_tranpose.conv.weight"], None, 2)  # layers.py:83,156 (attribute typo is the key)
+    if skip is None:  # skip_channels == 0, layers.py:158-159
+        return conv_block(P, k + ".conv_block", out, training)
+    if attention:  # layers.py:161-166
+        a = attention_layer(P, k + ".conv_o", out, training) + attention_layer(P, k + ".conv_s", skip, training)
+        psi = attention_layer(P, k + ".psi", F.relu(a), training)
+        skip = skip * torch.sigmoid(psi)
+    return conv_block(P, k + ".conv_block", torch.cat((out, skip), 1), training)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# encoders (external arithmetic restated)
+# --------------------------------------------------------------------------------------------------------------
+
+RESNEST = {"resnest50": ([3, 4, 6, 3], 32), "resnest101": ([3, 4, 23, 3], 64),
+           "resnest200": ([3, 24, 36, 3], 64), "resnest269": ([3, 30, 48, 8], 64)}
+RESNET = {"resnet50": [3, 4, 6, 3], "resnet101": [3, 4, 23, 3], "resnet152": [3, 8, 36, 3]}
+
+
+def encoder_channels(encoder):
+    """unet.py:49-54"""
+    if "resnest" in encoder:
+        return [64 if "50" in encoder else 128, 256, 512, 1024, 2048]
+    return [64, 256, 512, 1024, 2048]
+
+
+def _splat(P, k, x, training, dilation):
+    """SplAtConv2d, radix 2, cardinality 1 (ResNeSt paper sec. 3; call site unet.py:52)."""
+    y = F.conv2d(x, P[k + ".conv.weight"], None, 1, dilation, dilation, groups=2)
+    y = F.relu(_bn(P, k + ".bn0", y, training))
+    c = y.shape[1] // 2
+    x0, x1 = y[:, :c], y[:, c:]
+    gap = F.adaptive_avg_pool2d(x0 + x1, 1)
+    gap = F.conv2d(gap, P[k + ".fc1.weight"], P[k + ".fc1.bias"])
+    gap = F.relu(_bn(P, k + ".bn1", gap, training))
+    att = F.conv2d(gap, P[k + ".fc2.weight"], P[k + ".fc2.bias"])
+    b = att.shape[0]
+    att = torch.softmax(att.view(b, 1, 2, c).transpose(1, 2), 1).reshape(b, 2 * c, 1, 1)
+    return att[:, :c] * x0 + att[:, c:] * x1
+
+
+def _resnest_block(P, k, x, training, stride, dilation, is_first, has_down):
+    out = F.relu(_bn(P, k + ".bn1", F.conv2d(x, P[k + ".conv1.weight"]), training))
+    out = _splat(P, k + ".conv2", out, training, dilation)
+    if stride > 1 or is_first:  # avd, after the SplAt conv (avd_first=False)
+        out = F.avg_pool2d(out, 3, stride, 1)
+    out = _bn(P, k + ".bn3", F.conv2d(out, P[k + ".conv3.weight"]), training)
+    res = x
+    if has_down:  # avg_down shortcut: AvgPool(stride, ceil, no pad count) -> 1x1 -> BN
+        kk = stride if dilation == 1 else 1
+        if kk > 1:
+            res = F.avg_pool2d(res, kk, kk, 0, ceil_mode=True, count_include_pad=False)
+        res = _bn(P, k + ".downsample.2", F.conv2d(res, P[k + ".downsample.1.weight"]), training)
+    return F.relu(out + res)
+
+
+def _resnet_block(P, k, x, training, stride, dilation, has_down):
+    """torchvision Bottleneck (stride on the 3x3, v1.5).  call site unet.py:54-63"""
+    out = F.relu(_bn(P, k + ".bn1", F.conv2d(x, P[k + ".conv1.weight"]), training))
+    out = F.relu(_bn(P, k + ".bn2", F.conv2d(out, P[k + ".conv2.weight"], None, stride, dilation, dilation), training))
+    out = _bn(P, k + ".bn3", F.conv2d(out, P[k + ".conv3.weight"]), training)
+    res = x
+    if has_down:
+        res = _bn(P, k + ".downsample.1", F.conv2d(x, P[k + ".downsample.0.weight"], None, stride), training)
+    return F.relu(out + res)
+
+
+def _stage_plan(dilation):
+    """(stride, first-block dilation, other-block dilation) of layer1..4 for --dilation 1|2|4."""
+    if dilation == 1:
+        return [(1, 1, 1), (2, 1, 1), (2, 1, 1), (2, 1, 1)]
+    if dilation == 2:
+        return [(1, 1, 1), (2, 1, 1), (2, 1, 1), (1, 1, 2)]
+    return [(1, 1, 1), (2, 1, 1), (1, 1, 2), (1, 2, 4)]
+
+
+def encoder_forward(P, k, x, training, encoder, dilation=1):
+    """get_encoder's five stages (unet.py:80-84) applied in order; returns (enc1..enc5).
+
+    ``k`` is the prefix in front of ``enc_l1`` .. ``enc_l5`` (e.g. ``"unet."``); ``suffix`` variants are handled by callers.
+    """
+    return encoder_forward_named(P, [k + f"enc_l{i}" for i in range(1, 6)], x, training, encoder, dilation)
+
+
+def encoder_forward_named(P, names, x, training, encoder, dilation=1):
+    feats = []
+    for i in range(5):
+        x = encoder_stage(P, names[i], i, x, training, encoder, dilation)
+        feats.append(x)
+    return feats
+
+
+def encoder_stage(P, name, i, x, training, encoder, dilation=1):
+    """Stage ``i`` (0-based) of get_encoder: 0 = stem+bn1+relu, 1 = maxpool+layer1, 2..4 = layer2..4."""
+    is_st = "resnest" in encoder
+    blocks = RESNEST[encoder][0] if is_st else RESNET[encoder]
+    if i == 0:
+        if is_st:  # deep stem Sequential idx 0,1,3,4,6 then bn1 (name.1)
+            s = name + ".0"
+            x = F.relu(_bn(P, s + ".1", F.conv2d(x, P[s + ".0.weight"], None, 2, 1), training))
+            x = F.relu(_bn(P, s + ".4", F.conv2d(x, P[s + ".3.weight"], None, 1, 1), training))
+            x = F.conv2d(x, P[s + ".6.weight"], None, 1, 1)
+        else:
+            x = F.conv2d(x, P[name + ".0.weight"], P.get(name + ".0.bias"), 2, 3)
+        return F.relu(_bn(P, name + ".1", x, training))
+    plan = _stage_plan(dilation)
+    stride, d_first, d_rest = plan[i - 1]
+    if is_st:
+        # ResNeSt's dilation==2 path dilates layer4 blocks by 2 except the first (upstream _make_layer)
+        pre = name + ".1." if i == 1 else name + "."
+        if i == 1:
+            x = F.max_pool2d(x, 3, 2, 1)
+        for b in range(blocks[i - 1]):
+            if b == 0:
+                x = _resnest_block(P, pre + "0", x, training, stride, d_first, is_first=(i != 1), has_down=True)
+            else:
+                x = _resnest_block(P, pre + str(b), x, training, 1, d_rest, False, False)
+        return x
+    # torchvision replace_stride_with_dilation: first block keeps the previous dilation, the rest use the new one
+    # -- the same (stride, first, rest) plan as ResNeSt's.
+    pre = name + ".1." if i == 1 else name + "."
+    if i == 1:
+        x = F.max_pool2d(x, 3, 2, 1)
+    for b in range(blocks[i - 1]):
+        if b == 0:
+            x = _resnet_block(P, pre + "0", x, training, stride, d_first, has_down=True)
+        else:
+            x = _resnet_block(P, pre + str(b), x, training, 1, d_rest, False)
+    return x
+
+
+# --------------------------------------------------------------------------------------------------------------
+# U-Net assembly
+# --------------------------------------------------------------------------------------------------------------
+
+
+def decoder_forward(P, names, encs, training, attention):
+    """UNetTemplate.forward decoder half for dilation 1 (unet.py:153-159); names = dec_l1..dec_l5 prefixes."""
+    enc1, enc2, enc3, enc4, enc5 = encs
+    d1 = upsample_block(P, names[0], enc5, enc4, training, attention)
+    d2 = upsample_block(P, names[1], d1, enc3, training, attention)
+    d3 = upsample_block(P, names[2], d2, enc2, training, attention)
+    d4 = upsample_block(P, names[3], d3, enc1, training, attention)
+    d5 = upsample_block(P, names[4], d4, None, training, attention)
+    return d5, d4, d3
+
+
+def unet_template(P, k, x, training, args):
+    """UNetTemplate.forward, dilation 1, no ppm/aspp/interpolate (unet.py:136-172) -> (dec5, dec4, dec3)."""
+    encs = encoder_forward(P, k, x, training, args.encoder, 1)
+    return decoder_forward(P, [k + f"dec_l{i}" for i in range(1, 6)], encs, training, args.attention)
+
+
+def output_template(P, k, dec5, dec4, dec3, training, deep_supervision):
+    """OutputTemplate.forward (unet.py:191-197): 1x1 conv + bias heads; DS heads only in training."""
+    head = lambda n, t: F.conv2d(t, P[f"{k}.{n}.conv.weight"], P[f"{k}.{n}.conv.bias"])
+    out = head("output_block", dec5)
+    if training and deep_supervision:
+        return [out, head("output_block_ds4", dec4), head("output_block_ds3", dec3)]
+    return out
+
+
+def unet_loc(P, x, training, args, prefix=""):
+    """UNetLoc.forward (unet.py:212-215)."""
+    d5, d4, d3 = unet_template(P, prefix + "unet.", x, training, args)
+    return output_template(P, prefix + "output_block", d5, d4, d3, training, args.deep_supervision)
+
+
+def siamese_unet(P, x, training, args, prefix=""):
+    """SiameseUNet.forward (unet.py:231-236): the SAME U-Net on pre then post (separate BN statistics), cat, heads."""
+    pre = unet_template(P, prefix + "unet.", x[:, :3], training, args)
+    post = unet_template(P, prefix + "unet.", x[:, 3:], training, args)
+    d5, d4, d3 = (torch.cat([a, b], 1) for a, b in zip(pre, post))
+    return output_template(P, prefix + "output_block", d5, d4, d3, training, args.deep_supervision)
+
+
+def _fusion(P, k, pre, post, training):
+    """FusionBlock tail (layers.py:114-116): cat -> two ConvLayer(2C->C)."""
+    f = torch.cat([pre, post], 1)
+    return conv_layer(P, k + ".conv_pre", f, training), conv_layer(P, k + ".conv_post", f, training)
+
+
+def fused_unet(P, x, training, args, prefix=""):
+    """FusedUNet.forward (unet.py:360-376): twin encoders/decoders with cross-fusion after each of 10 stages."""
+    p = prefix
+    pre, post = x[:, :3], x[:, 3:]
+    e_pre, e_post = [], []
+    for i in range(5):
+        pre = encoder_stage(P, f"{p}enc_l{i+1}_pre", i, pre, training, args.encoder, 1)
+        post = encoder_stage(P, f"{p}enc_l{i+1}_post", i, post, training, args.encoder, 1)
+        pre, post = _fusion(P, f"{p}fusion_block{i+1}", pre, post, training)
+        e_pre.append(pre)
+        e_post.append(post)
+    d_pre, d_post = [], []
+    for i in range(5):
+        sk_pre = e_pre[3 - i] if i < 4 else None
+        sk_post = e_post[3 - i] if i < 4 else None
+        pre = upsample_block(P, f"{p}dec_l{i+1}_pre", pre, sk_pre, training, args.attention)
+        post = upsample_block(P, f"{p}dec_l{i+1}_post", post, sk_post, training, args.attention)
+        pre, post = _fusion(P, f"{p}fusion_block_dec{i+1}", pre, post, training)
+        d_pre.append(pre)
+        d_post.append(post)
+    d5, d4, d3 = (torch.cat([d_pre[j], d_post[j]], 1) for j in (4, 3, 2))
+    return output_template(P, p + "output_block", d5, d4, d3, training, args.deep_supervision)
+
+
+def model_forward(P, x, training, args, prefix=""):
+    """Model.__init__ dispatch (plt.py:26) for the variants BASELINE.json names."""
+    if args.type == "pre":
+        return unet_loc(P, x, training, args, prefix)
+    if args.dmg_model == "siamese":
+        return siamese_unet(P, x, training, args, prefix)
+    if args.dmg_model == "fused":
+        return fused_unet(P, x, training, args, prefix)
+    raise NotImplementedError(args.dmg_model)
+
+
+def tta_forward(P, x, args, prefix=""):
+    """Model.forward with --tta (plt.py:42-48): mean of logits over {id, flip H, flip W, flip HW}."""
+    pred = model_forward(P, x, False, args, prefix)
+    for dims in ([2], [3], [2, 3]):
+        pred = pred + torch.flip(model_forward(P, torch.flip(x, dims), False, args, prefix), dims)
+    return pred / 4
+
+
+# --------------------------------------------------------------------------------------------------------------
+# losses (loss.py) -- MONAI 0.4.0 formulas restated
+# --------------------------------------------------------------------------------------------------------------
+
+
+def dice_loss(logits2d, target1d, include_background):
+    """MonaiLoss('dice') on flattened (M, C) logits / (M,) labels: batch=True reduces over everything.  loss.py:12-13,17-20"""
+    p = torch.softmax(logits2d, 1)
+    t = F.one_hot(target1d, logits2d.shape[1]).to(p.dtype)
+    if not include_background:
+        p, t = p[:, 1:], t[:, 1:]
+    inter, denom = (p * t).sum(0), p.sum(0) + t.sum(0)
+    return (1 - (2 * inter + 1e-5) / (denom + 1e-5)).mean()
+
+
+def focal_loss(logits2d, target1d, gamma=2.0):
+    """MonaiLoss('focal'), gamma 2, mean over pixels.  loss.py:11,21"""
+    logpt = F.log_softmax(logits2d, 1).gather(1, target1d[:, None])[:, 0]
+    return (-(1 - logpt.exp()) ** gamma * logpt).mean()
+
+
+def ce_loss(logits2d, target1d):
+    return F.cross_entropy(logits2d, target1d)
+
+
+def loss_forward(y_pred, y_true, loss_str, post):
+    """Loss.forward (loss.py:85-101).  `post` keeps only pixels with label > 0 and shifts labels by -1.
+
+    'ohem' is the reference's effective behaviour: loss.py:45 slices the (values, indices) tuple so no negative is
+    ever dropped and the result is sum(CE)/N == mean CE.
+    """
+    c = y_pred.shape[1]
+    flat = y_pred.permute(0, 2, 3, 1).reshape(-1, c)
+    tgt = y_true.reshape(-1).long()
+    if post:
+        keep = tgt > 0
+        flat, tgt = flat[keep], tgt[keep] - 1
+    total = 0
+    for name in loss_str.split("+"):
+        if name == "dice":
+            total = total + dice_loss(flat, tgt, include_background=(c != 2))
+        elif name == "focal":
+            total = total + focal_loss(flat, tgt)
+        elif name in ("ce", "ohem"):
+            total = total + ce_loss(flat, tgt)
+        else:
+            raise NotImplementedError(name)
+    return total
+
+
+def compute_loss(preds, label, loss_str, post, deep_supervision):
+    """Model.compute_loss (plt.py:69-77): 1, 1/2, 1/4 weights on nearest-downsampled labels, normalised."""
+    if not deep_supervision:
+        return loss_forward(preds, label, loss_str, post)
+    loss = loss_forward(preds[0], label, loss_str, post)
+    for i, pred in enumerate(preds[1:]):
+        f = label.shape[-1] // pred.shape[-1]
+        loss = loss + 0.5 ** (i + 1) * loss_forward(pred, label[:, ::f, ::f], loss_str, post)  # F.interpolate nearest on u8
+    return loss / (2 - 2 ** (-len(preds)))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# metric, post-process, loader normalise
+# --------------------------------------------------------------------------------------------------------------
+
+
+def f1_counters(logits, targets, n_class):
+    """F1.update (utils/f1.py:28-42): returns (tp, fp, fn) int64 arrays of length n_class-1."""
+    pred = torch.argmax(torch.softmax(logits, 1), 1)
+    tgt = targets.long()
+    if n_class == 5:
+        pred = pred + 1
+        keep = tgt > 0
+        pred, tgt = pred[keep], tgt[keep]
+    tp, fp, fn = [], [], []
+    for c in range(1, n_class):
+        tp.append(int(((pred == c) & (tgt == c)).sum()))
+        fn.append(int(((pred != c) & (tgt == c)).sum()))
+        fp.append(int(((pred == c) & (tgt != c)).sum()))
+    return np.array(tp), np.array(fp), np.array(fn)
+
+
+def f1_compute(tp, fp, fn):
+    """F1.compute (utils/f1.py:44-49)."""
+    tp, fp, fn = (np.asarray(a, np.float32) for a in (tp, fp, fn))
+    f1 = 200 * tp / (2 * tp + fp + fn)
+    if len(tp) == 4:
+        return np.float32(4 / sum((f + np.float32(1e-6)) ** -1 for f in f1)), f1
+    return f1, None
+
+
+def post_process(loc, dmg):
+    """utils/post_process.py:27-38 without --components/--dilate: (pre u8, post u8) label maps."""
+    post = np.argmax(dmg, axis=0) + 1 if dmg.shape[0] == 4 else dmg
+    idx = np.logical_or(loc > 0.3, np.logical_and(loc > 0.1, post > 1))
+    pre = np.zeros(loc.shape)
+    pre[idx] = 1
+    post = post * pre
+    return pre.astype(np.uint8), post.astype(np.uint8)
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def normalize_tile(img_u8_hwc):
+    """A.Normalize() + HWC->CHW as TestDataset does (pytorch_loader.py:63,165,170): (x - 255*mean) * (1/(255*std)) in f32.
+
+    cv2 hands over BGR but the RGB ImageNet constants are applied by channel position (reference quirk).
+    """
+    mean = np.array(IMAGENET_MEAN, np.float32) * 255.0
+    inv = np.reciprocal(np.array(IMAGENET_STD, np.float32) * 255.0, dtype=np.float32)
+    x = (img_u8_hwc.astype(np.float32) - mean) * inv
+    return np.transpose(x, (2, 0, 1))
+
+
+def noam_lr(step, warmup_steps, total_steps, init_lr, max_lr, final_lr):
+    """NoamLR.step (utils/scheduler.py:45-59) for one param group."""
+    if step <= warmup_steps:
+        return init_lr + step * (max_lr - init_lr) / warmup_steps
+    if step <= total_steps:
+        gamma = (final_lr / max_lr) ** (1 / (total_steps - warmup_steps))
+        return max_lr * gamma ** (step - warmup_steps)
+    return final_lr
+
+
+def canonical_key(key):
+    """FusedUNet registers each stage twice (unet.py:326,333: enc_l1_pre IS fusion_block1.pre_conv): map the alias
+    spelling of a state_dict key to the canonical one."""
+    import re
+    key = re.sub(r"fusion_block_dec(\d)\.(pre|post)_conv\.", r"dec_l\1_\2.", key)
+    return re.sub(r"fusion_block(\d)\.(pre|post)_conv\.", r"enc_l\1_\2.", key)
+
+
+def deterministic_state(shapes, seed=1):
+    """Order-independent deterministic fill used by the golden fixtures: every tensor is drawn from its own
+    generator seeded by crc32(key)^seed, so the reference modules, this oracle and the CUDA path can be given
+    identical weights without shipping a 170 MB state_dict.  ``shapes``: {key: (shape, dtype)}.
+    """
+    import zlib
+    out = {}
+    for key in sorted(shapes):
+        shape, dtype = shapes[key]
+        canon = canonical_key(key)  # both aliases of a shared module receive the same values
+        g = torch.Generator().manual_seed((zlib.crc32(canon.encode()) ^ seed) & 0x7FFFFFFF)
+        if key.endswith("num_batches_tracked"):
+            t = torch.zeros(shape, dtype=dtype)
+        elif key.endswith("running_mean"):
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif key.endswith("running_var"):
+            t = 0.5 + torch.rand(shape, generator=g)
+        elif len(shape) == 1 and key.endswith("weight"):  # BN gamma
+            t = 0.5 + torch.rand(shape, generator=g)
+        elif key.endswith("bias"):
+            t = 0.1 * torch.randn(shape, generator=g)
+        else:  # conv / convT weight: He-style fan-in scaling keeps activations O(1) through 100+ layers
+            fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
+            t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+        out[key] = t.to(dtype)
+    return out
