@@ -1,0 +1,251 @@
+/* xv2.h -- C ABI of libxv2 (hand-written sm_100a CUDA for the xView2 segmentation hot path).
+ *
+ * The reference (michal2409/xView2) is pure Python: it has no FFI of its own.  Every entry point below replaces a
+ * library call the reference reaches through PyTorch (cuDNN / ATen / MONAI / numpy); the call site it replaces is
+ * cited per function as <reference file>:<line>.  The Python mirror of the reference's module API
+ * (xview2_b200/model/*.py) binds these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says host.
+ *  - activations are NHWC ("channels-last"), contiguous unless a pixel stride `ld*` (in elements) is given.
+ *  - conv weights are [K][R][S][C/groups] (the physical order of a channels-last OIHW tensor);
+ *    transposed-conv weights are [Cin][R][S][Cout] (channels-last physical order of torch's (Cin,Cout,R,S)).
+ *  - dtype: XV2_F32 or XV2_BF16 for activations/packed weights; accumulation is always fp32;
+ *    master weights, gradients of weights, BN statistics and losses are fp32 (statistic partials fp64).
+ *  - `stream` is a cudaStream_t passed as void*.  No call allocates, synchronises or touches the host.
+ *  - return 0 on success, a negative XV2_E* code on failure; xv2_last_error() gives the message (thread-local).
+ */
+#ifndef XV2_H
+#define XV2_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XV2_F32 0
+#define XV2_BF16 1
+
+#define XV2_OK 0
+#define XV2_EINVAL (-1)   /* bad argument / unsupported shape for this entry point */
+#define XV2_ECUDA (-2)    /* CUDA runtime / driver error */
+#define XV2_EUNSUPPORTED (-3) /* shape not eligible for the tensor-core path (caller uses the SIMT entry) */
+
+#define XV2_ACT_NONE 0
+#define XV2_ACT_RELU 1
+#define XV2_ACT_LRELU 2 /* negative slope 0.01, layers.py:94 */
+
+const char* xv2_last_error(void);
+int xv2_version(void);
+/* Loads the driver entry point for tensor-map encoding and checks the device is sm_100. */
+int xv2_init(int device);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Convolution geometry shared by the SIMT and tensor-core entry points.
+ *   out[n,oh,ow,k] = sum_{r,s,c} src[n, ih, iw, g*Cg + c] * w[k][r][s][c]
+ *   with  num_h = oh*stride - pad + r*dil ;  taken only if num_h % ups == 0 ; ih = num_h / ups ; 0 <= ih < h
+ * `ups` = 1 is an ordinary convolution; ups > 1 expresses transposed convolution / strided dgrad as a gather.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct xv2_conv_geom {
+  int32_t n, h, w, c;       /* source tensor NHWC, c = all source channels */
+  int32_t oh, ow, k;        /* output tensor, k = all output channels */
+  int32_t r, s;             /* taps */
+  int32_t stride, pad, dil; /* square */
+  int32_t ups;              /* source up-sampling factor (1 = none) */
+  int32_t groups;
+  int32_t dtype;            /* XV2_F32 | XV2_BF16 : source, weights */
+  int32_t out_dtype;        /* XV2_F32 | XV2_BF16 : output */
+} xv2_conv_geom;
+
+/* SIMT (CUDA-core, fp32 accumulate) gather convolution: any stride/dilation/groups/channel count.
+ * Replaces nn.Conv2d / nn.ConvTranspose2d forward and data-gradient: layers.py:83,92,71,180; unet.py:52 (encoder).
+ * bias: fp32 [k] or NULL. */
+int xv2_conv_gather_simt(const xv2_conv_geom* g, const void* src, const void* w, const float* bias, void* out,
+                         void* stream);
+
+/* SIMT weight gradient: dw[k][r][s][c] (fp32, ACCUMULATED into dw with atomics: caller zero-fills) =
+ * sum_{n,oh,ow} dout[n,oh,ow,k] * src[n,ih,iw,g*Cg+c]; same index rule as above.  dout has geom.out dims, dtype `dtype`. */
+int xv2_conv_wgrad_simt(const xv2_conv_geom* g, const void* src, const void* dout, float* dw, void* stream);
+
+/* Sum over pixels of a [pixels][k] tensor -> fp32 [k] (bias gradient of the 1x1 output head, layers.py:180). */
+int xv2_colsum(const void* x, int64_t pixels, int32_t k, int32_t dtype, float* out, void* stream);
+
+/* fp32 master weight [A][R][S][B] (physical channels-last OIHW, A = all out channels, B = in per group) ->
+ * packed `dst_dtype` weight.  mode 0: same order.  mode 1: dgrad / transposed-conv order
+ * dst[g*B + b][R-1-r][S-1-s][a_in_group] (flipped taps, in/out swapped per group).
+ * mode 2: dst[r][s][b][a] (transposed-conv GEMM rows for xv2_conv_tc convt=1; groups must be 1). */
+int xv2_pack_weight(const float* src, void* dst, int32_t a, int32_t r, int32_t s, int32_t b, int32_t groups,
+                    int32_t mode, int32_t dst_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05 + TMEM + TMA) implicit-GEMM convolution, bf16 in / fp32 accumulate.
+ * Stride-1 "same" convolutions only (3x3 p=dil, 1x1), groups allowed, optional second source that is
+ * concatenated on the channel axis WITHOUT materialising torch.cat (layers.py:167 / layers.py:114),
+ * and the 2x2 stride-2 transposed convolution as GEMM + pixel-shuffle store (layers.py:83).
+ * Returns XV2_EUNSUPPORTED when the shape is not eligible (caller falls back to the SIMT entry).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct xv2_tc_conv {
+  int32_t n, h, w;          /* spatial dims of sources (and of the output unless convt) */
+  int32_t c0, c1;           /* channels of source 0 / source 1 (c1 = 0: single source), per tensor */
+  int32_t ld0, ld1;         /* pixel stride (elements) of the sources; 0 = contiguous (= c0 / c1) */
+  int32_t k;                /* output channels (all groups) */
+  int32_t r, s, pad, dil;   /* taps, padding, dilation (stride is 1) */
+  int32_t groups;           /* c1 must be 0 when groups > 1 */
+  int32_t convt;            /* 1: w is [4*k][c0] (tap-major rows), out is (n, 2h, 2w, k): 2x2 s2 transposed conv
+                             * 2: its data gradient: src0 is (n, 2h, 2w, c0), w is [k][2][2][c0], out is (n, h, w, k) */
+  int32_t out_dtype;        /* XV2_BF16 | XV2_F32 */
+  int32_t ldo;              /* output pixel stride in elements; 0 = k */
+} xv2_tc_conv;
+
+/* w: bf16 [k][r][s][(c0+c1)/groups] (convt: [2][2][k][c0]); bias fp32 [k] or NULL.
+ * stats: optional fp64 [2*k] accumulators (sum, sum of squares of the ROUNDED outputs per channel), caller zero-fills:
+ *        the batch-norm statistics of nn.BatchNorm2d (layers.py:93) fused into the conv epilogue. */
+int xv2_conv_tc(const xv2_tc_conv* p, const void* src0, const void* src1, const void* w, const float* bias,
+                void* out, double* stats, void* stream);
+
+/* Tensor-core weight gradient: dw[k][r][s][c] fp32 (accumulated with atomics; caller zero-fills), bf16 operands.
+ * src0/src1 as above (c split the same way), dout [n][h][w][k] with pixel stride lddo (0 = k).
+ * convt = 1: dw is [c0(row)][2][2][k]: gradient of the transposed conv given x = src0 (n,h,w,c0), dout (n,2h,2w,k). */
+int xv2_wgrad_tc(const xv2_tc_conv* p, const void* src0, const void* src1, const void* dout, int32_t lddo,
+                 float* dw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Batch normalisation (+ activation, + residual), NHWC.   nn.BatchNorm2d: layers.py:93,72; encoder BNs unet.py:52
+ * ---------------------------------------------------------------------------------------------------------- */
+/* per-channel sum and sum of squares over pixels -> fp64 stats[2*c] (accumulated; caller zero-fills) */
+int xv2_bn_stats(const void* x, int64_t pixels, int32_t c, int32_t dtype, double* stats, void* stream);
+/* training: stats -> mean/invstd (saved, fp32 [c] each), scale/shift (fp32 [c] each), running stats update
+ * (momentum, unbiased variance).  count = pixels the stats were taken over. */
+int xv2_bn_finalize(const double* stats, int64_t count, int32_t c, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, float* mean, float* invstd,
+                    float* scale, float* shift, void* stream);
+/* eval: scale/shift from running statistics */
+int xv2_bn_eval_coeffs(int32_t c, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, void* stream);
+/* y = act(scale*x + shift (+ residual)) */
+int xv2_bn_apply(const void* x, const void* residual, void* y, int64_t pixels, int32_t c, int32_t dtype,
+                 const float* scale, const float* shift, int32_t act, void* stream);
+/* backward pass 1: through the activation (recomputed from x, scale, shift, residual) then the two BN reductions.
+ * red (fp64 [2*c], accumulated; caller zero-fills) = (sum du, sum du * xhat).  */
+int xv2_bn_bwd_reduce(const void* dy, const void* x, const void* residual, int64_t pixels, int32_t c, int32_t dtype,
+                      const float* scale, const float* shift, const float* mean, const float* invstd, int32_t act,
+                      double* red, void* stream);
+/* backward pass 2: dx = gamma*invstd*(du - mean(du) - xhat*mean(du*xhat)) [train] or du*scale [eval: red == NULL];
+ * dres (optional) = du; dgamma/dbeta (fp32 [c], written) from red. */
+int xv2_bn_bwd_apply(const void* dy, const void* x, const void* residual, void* dx, void* dres, int64_t pixels,
+                     int32_t c, int32_t dtype, const float* scale, const float* shift, const float* mean,
+                     const float* invstd, const float* gamma, int32_t act, const double* red, int64_t count,
+                     float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Pooling, NHWC.  nn.MaxPool2d(3,2,1) unet.py:81; ResNeSt avd AvgPool2d(3,s,1) and avg-down AvgPool2d(s,s,ceil) unet.py:52
+ * ---------------------------------------------------------------------------------------------------------- */
+int xv2_maxpool_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh, int32_t ow,
+                    int32_t k, int32_t stride, int32_t pad, int32_t dtype, void* stream);
+/* recomputes the arg-max from x (first maximum in scan order, like ATen) and scatters dy; dx is fully written */
+int xv2_maxpool_bwd(const void* x, const void* dy, void* dx, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh,
+                    int32_t ow, int32_t k, int32_t stride, int32_t pad, int32_t dtype, void* stream);
+int xv2_avgpool_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh, int32_t ow,
+                    int32_t k, int32_t stride, int32_t pad, int32_t count_include_pad, int32_t dtype, void* stream);
+int xv2_avgpool_bwd(const void* dy, void* dx, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh, int32_t ow,
+                    int32_t k, int32_t stride, int32_t pad, int32_t count_include_pad, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Split attention (ResNeSt SplAtConv2d, radix 2, cardinality 1; call site unet.py:52)
+ * x is [n][hw][2*c] (radix-major channel halves).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* gap[n][c] (fp32) = mean_hw (x[..,c] + x[..,c+C]) */
+int xv2_splat_gap(const void* x, float* gap, int32_t n, int64_t hw, int32_t c, int32_t dtype, void* stream);
+/* att[n][2c] (fp32) = softmax over the radix pair of logits[n][2c] */
+int xv2_rsoftmax_fwd(const float* logits, float* att, int32_t n, int32_t c, void* stream);
+int xv2_rsoftmax_bwd(const float* att, const float* datt, float* dlogits, int32_t n, int32_t c, void* stream);
+/* out[n][hw][c] = att[n][c]*x[..,c] + att[n][C+c]*x[..,C+c] */
+int xv2_splat_combine(const void* x, const float* att, void* out, int32_t n, int64_t hw, int32_t c, int32_t dtype,
+                      void* stream);
+/* datt[n][2c] (fp32, accumulated; caller zero-fills) = sum_hw dout[..,c] * x[..,r*C+c] */
+int xv2_splat_bwd_att(const void* x, const void* dout, float* datt, int32_t n, int64_t hw, int32_t c, int32_t dtype,
+                      void* stream);
+/* dx[n][hw][2c] = att[n][r*C+c]*dout[..,c] + dgap[n][c]/hw */
+int xv2_splat_bwd_x(const void* dout, const float* att, const float* dgap, void* dx, int32_t n, int64_t hw,
+                    int32_t c, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Element-wise helpers
+ * ---------------------------------------------------------------------------------------------------------- */
+/* y = a + b (optionally relu) ; backward of relu handled by xv2_relu_bwd */
+int xv2_add_act(const void* a, const void* b, void* y, int64_t numel, int32_t dtype, int32_t act, void* stream);
+/* dx = dy * (y > 0 ? 1 : slope(act)) */
+int xv2_act_bwd(const void* dy, const void* y, void* dx, int64_t numel, int32_t dtype, int32_t act, void* stream);
+/* attention gate (layers.py:165-166): out[p][c] = skip[p][c] * sigmoid(psi[p]);  psi is [pixels] in `dtype` */
+int xv2_gate_fwd(const void* skip, const void* psi, void* out, int64_t pixels, int32_t c, int32_t dtype, void* stream);
+/* dskip = dout*sig ; dpsi[p] = sig*(1-sig) * sum_c dout[p][c]*skip[p][c] */
+int xv2_gate_bwd(const void* dout, const void* skip, const void* psi, void* dskip, void* dpsi, int64_t pixels,
+                 int32_t c, int32_t dtype, void* stream);
+/* flip an NHWC tensor along H and/or W (TTA, plt.py:30,46) */
+int xv2_flip(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t flip_h, int32_t flip_w,
+             int32_t dtype, void* stream);
+/* dst (bf16|f32) <- src (bf16|f32) element-wise cast */
+int xv2_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t numel, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Loss, metric, post-process.  logits are fp32 NHWC [n][h][w][ncls]; labels uint8 [n][H][W] sampled with stride
+ * `lstride` (deep supervision nearest down-sampling, plt.py:73: label[::f, ::f]).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define XV2_LOSS_DICE 1
+#define XV2_LOSS_FOCAL 2
+#define XV2_LOSS_CE 4 /* 'ce' and the reference's effective 'ohem' (loss.py:45 never truncates) */
+
+/* pass 1: partial sums.  sums fp64 [3*ncls + 3], accumulated (caller zero-fills):
+ *   [0..ncls) sum p_c*t_c   [ncls..2ncls) sum p_c   [2ncls..3ncls) sum t_c   then focal sum, ce sum, pixel count.
+ * post != 0: only pixels with label > 0 count and labels are shifted by -1 (loss.py:86-90). */
+int xv2_loss_partials(const float* logits, const uint8_t* labels, int32_t n, int32_t h, int32_t w, int32_t ncls,
+                      int32_t lstride, int32_t post, double* sums, void* stream);
+/* pass 2: loss[0] (fp32) += weight * (selected terms); terms = OR of XV2_LOSS_*  (loss.py:98-101, plt.py:74-76).
+ * Also writes coef (fp32 [2*ncls + 4]) used by the backward kernel. */
+int xv2_loss_finalize(const double* sums, int32_t ncls, int32_t terms, float weight, float* loss, float* coef,
+                      void* stream);
+/* backward: dlogits = dloss[0] * d(loss)/d(logits), one pass */
+int xv2_loss_backward(const float* logits, const uint8_t* labels, int32_t n, int32_t h, int32_t w, int32_t ncls,
+                      int32_t lstride, int32_t post, int32_t terms, const float* coef, const float* dloss,
+                      float* dlogits, void* stream);
+
+/* F1.update (utils/f1.py:28-42): counters int64 [3*(ncls_metric-1)] = tp | fp | fn, accumulated.
+ * ncls_metric 2: pred = argmax(logits[2]); 5: logits have 4 channels, pred = argmax+1, only pixels with label > 0.
+ * Optionally writes the uint8 prediction map (argmax, lowest index wins ties). */
+int xv2_f1_update(const float* logits, const uint8_t* labels, int64_t pixels, int32_t ncls_metric, int64_t* counters,
+                  uint8_t* pred_map, void* stream);
+/* mean over TTA passes folded into the consumer: out = (a + b + c + d) * 0.25 (plt.py:44-47) */
+int xv2_mean4(const float* a, const float* b, const float* c, const float* d, float* out, int64_t numel, void* stream);
+/* Model.save + utils/post_process.py:27-38 fused: from localisation logits (2 ch) and damage logits (4 ch):
+ *   loc = sigmoid(loc_logit[1]); post = argmax(softmax(dmg)) + 1; pre = loc>0.3 | (loc>0.1 & post>1); post *= pre. */
+int xv2_post_process(const float* loc_logits, const float* dmg_logits, int64_t pixels, uint8_t* pre_map,
+                     uint8_t* post_map, void* stream);
+/* same rule from probabilities as post_process.py reads them from .npy: loc [pixels], dmg [4][pixels] (planar) */
+int xv2_post_process_probs(const float* loc, const float* dmg, int64_t pixels, uint8_t* pre_map, uint8_t* post_map,
+                           void* stream);
+
+/* 1x1 output head (layers.py:180): logits[p][ncls] (fp32) = x[p][c] . w[ncls][c] + b ; ncls <= 8 */
+int xv2_head_fwd(const void* x, const float* w, const float* b, float* logits, int64_t pixels, int32_t c,
+                 int32_t ncls, int32_t dtype, void* stream);
+/* dx[p][c] = sum_k dlogits[p][k] w[k][c] ; dw[ncls][c], db[ncls] fp32 accumulated (caller zero-fills) */
+int xv2_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, float* dw, float* db, int64_t pixels,
+                 int32_t c, int32_t ncls, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Loader: decoded uint8 HWC tiles (cv2 BGR order, pytorch_loader.py:40) -> normalised NHWC activations
+ * (A.Normalize, pytorch_loader.py:63: (x - 255*mean) * (1/(255*std)), constants applied by channel position).
+ * pre (and optional post) are [n][h][w][3] uint8; out is [n][h][w][3 or 6].
+ * ---------------------------------------------------------------------------------------------------------- */
+int xv2_normalize_tiles(const uint8_t* pre, const uint8_t* post, void* out, int32_t n, int32_t h, int32_t w,
+                        int32_t out_dtype, void* stream);
+
+/* Fused AdamW over one flat parameter (torch.optim.AdamW semantics, plt.py:154): step is 1-based. */
+int xv2_adamw(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1, float beta2,
+              float eps, float weight_decay, int32_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XV2_H */

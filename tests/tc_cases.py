@@ -1,0 +1,95 @@
+"""Tensor-core (tcgen05) convolution cases, shared by tests/test_tc_gpu.py and tools/tc_probe.py.
+
+Every case runs the op through xview2_b200.ops with the tensor-core path enabled and compares forward, data gradient
+and weight gradient with torch's fp32 convolution on the same bf16-rounded inputs.  `lib.launches()` bookkeeping plus a
+direct check of the entry-point return code make sure the tcgen05 kernel (not the SIMT fallback) produced the result.
+"""
+import torch
+import torch.nn.functional as F
+
+CL = torch.channels_last
+
+# name: (kind, n, c0, c1, h, w, k, r, dil, groups)
+CASES = {
+    "c64_k64_3x3_w16": ("conv", 2, 64, 0, 16, 16, 64, 3, 1, 1),
+    "c64_k256_1x1_w32": ("conv", 2, 64, 0, 32, 32, 256, 1, 1, 1),
+    "c32_k32_3x3_w128": ("conv", 1, 32, 0, 8, 128, 32, 3, 1, 1),
+    "c32_k64_3x3_w64": ("conv", 2, 32, 0, 8, 64, 64, 3, 1, 1),
+    "c128_k512_1x1_w8": ("conv", 2, 128, 0, 16, 8, 512, 1, 1, 1),
+    "g2_c64_k128_3x3": ("conv", 2, 64, 0, 16, 16, 128, 3, 1, 2),       # SplAt radix conv, 32 ch / group
+    "g2_c128_k256_3x3": ("conv", 2, 128, 0, 16, 16, 256, 3, 1, 2),
+    "cat_64_128_k64_3x3": ("conv", 2, 64, 128, 16, 16, 64, 3, 1, 1),   # decoder conv over (up, skip)
+    "cat_32_32_k32_3x3": ("conv", 2, 32, 32, 16, 32, 32, 3, 1, 1),
+    "dil2_c64_k64": ("conv", 1, 64, 0, 16, 16, 64, 3, 2, 1),
+    "c256_k96_3x3_w256": ("conv", 1, 256, 0, 2, 256, 96, 3, 1, 1),     # N tile not a power of two
+    "convt_c128_k64": ("convt", 2, 128, 0, 16, 16, 64, 2, 1, 1),
+    "convt_c64_k32_w64": ("convt", 1, 64, 0, 8, 64, 32, 2, 1, 1),
+    "convt_c2048_k512": ("convt", 1, 2048, 0, 16, 8, 512, 2, 1, 1),
+}
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def _rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def run_case(name, check_wgrad=True, check_dgrad=True):
+    """Returns dict(fwd=, dgrad=, wgrad=) of relative errors; raises if the tensor-core entry declined the shape."""
+    from xview2_b200 import lib, ops
+    kind, n, c0, c1, h, w, k, r, dil, groups = CASES[name]
+    ops.USE_TENSOR_CORES = True
+    calls = []
+    orig_call = ops.call
+
+    def spy(fn, *a, **kw):
+        rc = orig_call(fn, *a, **kw)
+        calls.append((fn, rc))
+        return rc
+
+    ops.call = spy
+    try:
+        x = _rnd((n, c0, h, w), 1).to(torch.bfloat16).contiguous(memory_format=CL).requires_grad_(True)
+        x2 = _rnd((n, c1, h, w), 2).to(torch.bfloat16).contiguous(memory_format=CL).requires_grad_(True) if c1 else None
+        if kind == "conv":
+            cg = (c0 + c1) // groups
+            wt = _rnd((k, cg, r, r), 3, (2.0 / (cg * r * r)) ** 0.5).contiguous(memory_format=CL).requires_grad_(True)
+            pad = dil * (r - 1) // 2
+            y = ops.conv2d(x, wt, None, 1, pad, dil, groups, x2)
+        else:
+            wt = _rnd((c0, k, 2, 2), 3, (1.0 / c0) ** 0.5).contiguous(memory_format=CL).requires_grad_(True)
+            y = ops.conv_transpose2x2(x, wt)
+        gy = _rnd(tuple(y.shape), 4).to(torch.bfloat16).contiguous(memory_format=CL)
+        y.backward(gy)
+        torch.cuda.synchronize()
+    finally:
+        ops.call = orig_call
+    tc_calls = [(f, rc) for f, rc in calls if f in ("xv2_conv_tc", "xv2_wgrad_tc")]
+    declined = [(f, rc) for f, rc in tc_calls if rc != 0]
+    if declined or not tc_calls:
+        raise AssertionError(f"{name}: tensor-core entry declined or not used: {tc_calls} ({lib.last_error()})")
+    xr = x.detach().float().requires_grad_(True)
+    wr = wt.detach().to(torch.bfloat16).float().requires_grad_(True)
+    if kind == "conv":
+        src = xr
+        x2r = None
+        if c1:
+            x2r = x2.detach().float().requires_grad_(True)
+            src = torch.cat((xr, x2r), 1)
+        yr = F.conv2d(src, wr, None, 1, pad, dil, groups)
+    else:
+        x2r = None
+        yr = F.conv_transpose2d(xr, wr, None, 2)
+    yr.backward(gy.float())
+    out = {"fwd": rel(y, yr)}
+    if check_dgrad:
+        out["dgrad"] = rel(x.grad, xr.grad)
+        if c1:
+            out["dgrad2"] = rel(x2.grad, x2r.grad)
+    if check_wgrad:
+        out["wgrad"] = rel(wt.grad, wr.grad)
+    return out

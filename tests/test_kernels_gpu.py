@@ -1,0 +1,329 @@
+"""GPU unit tests (-m gpu): every libxv2 operator against a plain PyTorch fp32 reference of the same op.
+
+Tolerances: fp32 path 1e-4 relative (accumulation order only); bf16 path 2e-2 relative to the tensor's max
+(bf16 has 8 mantissa bits; inputs are rounded to bf16 first so only accumulation/rounding of outputs differ).
+Integer / label outputs (argmax maps, F1 counters, post-process) are compared bit-exactly.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CL = torch.channels_last
+
+
+def _ops():
+    from xview2_b200 import ops
+    return ops
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(*shape, generator=g) * scale
+    return t.to(dtype).cuda()
+
+
+def tol(dtype):
+    return 1e-4 if dtype == torch.float32 else 2e-2
+
+
+CONV_CASES = [
+    # n, c, h, w, k, r, stride, pad, dil, groups
+    (2, 3, 32, 32, 32, 3, 2, 1, 1, 1),      # ResNeSt stem conv1
+    (2, 3, 32, 32, 64, 7, 2, 3, 1, 1),      # ResNet stem
+    (2, 32, 16, 16, 64, 3, 1, 1, 1, 1),
+    (2, 64, 16, 16, 128, 3, 1, 1, 1, 2),    # SplAt grouped conv
+    (2, 64, 16, 16, 64, 3, 2, 1, 1, 1),     # ResNet strided 3x3
+    (2, 128, 8, 8, 256, 1, 1, 0, 1, 1),
+    (2, 128, 16, 16, 256, 1, 2, 0, 1, 1),   # ResNet strided 1x1 downsample
+    (1, 64, 16, 16, 64, 3, 1, 2, 2, 1),     # dilated
+    (3, 40, 9, 11, 24, 3, 1, 1, 1, 1),      # ragged sizes
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_simt_fwd_bwd(case, dtype):
+    ops = _ops()
+    n, c, h, w, k, r, stride, pad, dil, groups = case
+    x = rnd(n, c, h, w, dtype=dtype, seed=1).contiguous(memory_format=CL).requires_grad_(True)
+    wt = rnd(k, c // groups, r, r, seed=2, scale=(2.0 / (c // groups * r * r)) ** 0.5).contiguous(memory_format=CL).requires_grad_(True)
+    b = rnd(k, seed=3).requires_grad_(True)
+    old = ops.USE_TENSOR_CORES
+    ops.USE_TENSOR_CORES = False
+    try:
+        y = ops.conv2d(x, wt, b, stride, pad, dil, groups)
+        gy = rnd(*y.shape, dtype=dtype, seed=4)
+        y.backward(gy)
+    finally:
+        ops.USE_TENSOR_CORES = old
+    xr = x.detach().float().requires_grad_(True)
+    wr = (wt.detach().to(dtype).float() if dtype != torch.float32 else wt.detach().clone()).requires_grad_(True)
+    br = b.detach().clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, stride, pad, dil, groups)
+    yr.backward(gy.float())
+    t = tol(dtype)
+    assert rel(y, yr) < t
+    assert rel(x.grad, xr.grad) < t
+    assert rel(wt.grad, wr.grad) < t
+    assert rel(b.grad, br.grad) < t
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_transpose_simt(dtype):
+    ops = _ops()
+    x = rnd(2, 32, 8, 8, dtype=dtype, seed=1).contiguous(memory_format=CL).requires_grad_(True)
+    wt = rnd(32, 16, 2, 2, seed=2, scale=0.2).contiguous(memory_format=CL).requires_grad_(True)
+    old = ops.USE_TENSOR_CORES
+    ops.USE_TENSOR_CORES = False
+    try:
+        y = ops.conv_transpose2x2(x, wt)
+        gy = rnd(*y.shape, dtype=dtype, seed=4)
+        y.backward(gy)
+    finally:
+        ops.USE_TENSOR_CORES = old
+    xr = x.detach().float().requires_grad_(True)
+    wr = (wt.detach().to(dtype).float()).requires_grad_(True)
+    yr = F.conv_transpose2d(xr, wr, None, 2)
+    yr.backward(gy.float())
+    t = tol(dtype)
+    assert rel(y, yr) < t and rel(x.grad, xr.grad) < t and rel(wt.grad, wr.grad) < t
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("act,with_res", [(0, False), (1, False), (2, False), (1, True)])
+@pytest.mark.parametrize("c", [32, 20])
+def test_batch_norm_act(dtype, training, act, with_res, c):
+    ops = _ops()
+    bn = torch.nn.BatchNorm2d(c).cuda()
+    bn.weight.data = rnd(c, seed=5) * 0.2 + 1
+    bn.bias.data = rnd(c, seed=6) * 0.2
+    bn.running_mean.data = rnd(c, seed=7) * 0.1
+    bn.running_var.data = rnd(c, seed=8).abs() + 0.5
+    bn.train(training)
+    ref = torch.nn.BatchNorm2d(c).cuda()
+    ref.load_state_dict(bn.state_dict())
+    ref.train(training)
+    x = rnd(4, c, 12, 10, dtype=dtype, seed=1).contiguous(memory_format=CL).requires_grad_(True)
+    res = rnd(4, c, 12, 10, dtype=dtype, seed=2).contiguous(memory_format=CL).requires_grad_(True) if with_res else None
+    y = ops.batch_norm_act(x, bn, act, res)
+    gy = rnd(*y.shape, dtype=dtype, seed=3)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    rr = res.detach().float().requires_grad_(True) if with_res else None
+    u = ref(xr)
+    if with_res:
+        u = u + rr
+    yr = u if act == 0 else (F.relu(u) if act == 1 else F.leaky_relu(u, 0.01))
+    yr.backward(gy.float())
+    t = tol(dtype)
+    assert rel(y, yr) < t
+    assert rel(x.grad, xr.grad) < t * 2
+    assert rel(bn.weight.grad, ref.weight.grad) < t * 2 and rel(bn.bias.grad, ref.bias.grad) < t * 2
+    if with_res:
+        assert rel(res.grad, rr.grad) < t
+    if training:
+        assert rel(bn.running_mean, ref.running_mean) < 1e-3 and rel(bn.running_var, ref.running_var) < 1e-3
+        assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pools(dtype):
+    ops = _ops()
+    t = tol(dtype)
+    x = rnd(2, 16, 15, 18, dtype=dtype, seed=1).contiguous(memory_format=CL).requires_grad_(True)
+    xr = x.detach().float().requires_grad_(True)
+    for fn, rf in [
+        (lambda a: ops.max_pool2d(a, 3, 2, 1), lambda a: F.max_pool2d(a, 3, 2, 1)),
+        (lambda a: ops.avg_pool2d(a, 3, 2, 1), lambda a: F.avg_pool2d(a, 3, 2, 1)),
+        (lambda a: ops.avg_pool2d(a, 3, 1, 1), lambda a: F.avg_pool2d(a, 3, 1, 1)),
+        (lambda a: ops.avg_pool2d(a, 2, 2, 0, True, False), lambda a: F.avg_pool2d(a, 2, 2, 0, True, False)),
+    ]:
+        x.grad = None
+        xr.grad = None
+        y, yr = fn(x), rf(xr)
+        assert y.shape == yr.shape
+        gy = rnd(*y.shape, dtype=dtype, seed=9)
+        y.backward(gy)
+        yr.backward(gy.float())
+        assert rel(y, yr) < t and rel(x.grad, xr.grad) < t
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("training", [True, False])
+def test_split_attention(dtype, training):
+    ops = _ops()
+    c, n = 32, 3
+    fc1 = torch.nn.Conv2d(c, 32, 1).cuda()
+    bn1 = torch.nn.BatchNorm2d(32).cuda()
+    fc2 = torch.nn.Conv2d(32, 2 * c, 1).cuda()
+    bn1.running_var.data.fill_(0.7)
+    bn1.train(training)
+    x = rnd(n, 2 * c, 6, 5, dtype=dtype, seed=1).contiguous(memory_format=CL).requires_grad_(True)
+    out = ops.split_attention(x, fc1, bn1, fc2)
+    gy = rnd(*out.shape, dtype=dtype, seed=2)
+    out.backward(gy)
+    got = {k: p.grad.clone() for k, p in [("w1", fc1.weight), ("b1", fc1.bias), ("g", bn1.weight), ("b", bn1.bias),
+                                          ("w2", fc2.weight), ("b2", fc2.bias)]}
+    for p in (fc1.weight, fc1.bias, bn1.weight, bn1.bias, fc2.weight, fc2.bias):
+        p.grad = None
+    bn1.running_mean.data.zero_()
+    bn1.running_var.data.fill_(0.7)
+    xr = x.detach().float().requires_grad_(True)
+    x0, x1 = xr[:, :c], xr[:, c:]
+    gap = F.adaptive_avg_pool2d(x0 + x1, 1)
+    a = fc2(F.relu(bn1(fc1(gap))))
+    a = torch.softmax(a.view(n, 1, 2, c).transpose(1, 2), 1).reshape(n, 2 * c, 1, 1)
+    yr = a[:, :c] * x0 + a[:, c:] * x1
+    yr.backward(gy.float())
+    t = tol(dtype)
+    assert rel(out, yr) < t
+    assert rel(x.grad, xr.grad) < t * 2
+    assert rel(got["w2"], fc2.weight.grad) < t * 3 and rel(got["b2"], fc2.bias.grad) < t * 3
+    assert rel(got["w1"], fc1.weight.grad) < t * 3
+    assert rel(got["g"], bn1.weight.grad) < t * 3 and rel(got["b"], bn1.bias.grad) < t * 3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_elementwise(dtype):
+    ops = _ops()
+    t = tol(dtype)
+    a = rnd(2, 16, 7, 9, dtype=dtype, seed=1).contiguous(memory_format=CL).requires_grad_(True)
+    b = rnd(2, 16, 7, 9, dtype=dtype, seed=2).contiguous(memory_format=CL).requires_grad_(True)
+    y = ops.add_act(a, b, 1)
+    gy = rnd(*y.shape, dtype=dtype, seed=3)
+    y.backward(gy)
+    ar, br = a.detach().float().requires_grad_(True), b.detach().float().requires_grad_(True)
+    yr = F.relu(ar + br)
+    yr.backward(gy.float())
+    assert rel(y, yr) < t and rel(a.grad, ar.grad) < t and rel(b.grad, br.grad) < t
+    # attention gate
+    skip = rnd(2, 16, 7, 9, dtype=dtype, seed=4).contiguous(memory_format=CL).requires_grad_(True)
+    psi = rnd(2, 1, 7, 9, dtype=dtype, seed=5).contiguous(memory_format=CL).requires_grad_(True)
+    o = ops.gate(skip, psi)
+    o.backward(gy)
+    sr, pr = skip.detach().float().requires_grad_(True), psi.detach().float().requires_grad_(True)
+    orf = sr * torch.sigmoid(pr)
+    orf.backward(gy.float())
+    assert rel(o, orf) < t and rel(skip.grad, sr.grad) < t and rel(psi.grad, pr.grad) < t * 2
+    # flips are exact
+    for dims in ([2], [3], [2, 3]):
+        assert torch.equal(ops.flip(a.detach(), dims), torch.flip(a.detach(), dims))
+    # cast
+    f = rnd(2, 3, 8, 8, seed=6)
+    assert torch.equal(ops.cast(f, torch.bfloat16), f.to(torch.bfloat16).contiguous(memory_format=CL))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("ncls", [2, 4])
+def test_head(dtype, ncls):
+    ops = _ops()
+    x = rnd(2, 32, 16, 16, dtype=dtype, seed=1).contiguous(memory_format=CL).requires_grad_(True)
+    w = rnd(ncls, 32, 1, 1, seed=2, scale=0.2).requires_grad_(True)
+    b = rnd(ncls, seed=3).requires_grad_(True)
+    y = ops.head(x, w, b)
+    assert y.dtype == torch.float32
+    gy = rnd(*y.shape, seed=4)
+    y.backward(gy)
+    xr, wr, br = x.detach().float().requires_grad_(True), w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br)
+    yr.backward(gy)
+    t = tol(dtype)
+    assert rel(y, yr) < 1e-4 and rel(x.grad, xr.grad) < t and rel(w.grad, wr.grad) < 1e-3 and rel(b.grad, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("loss_str,ncls,post", [("focal+dice", 2, False), ("dice", 2, False), ("focal", 4, True),
+                                                 ("focal+dice", 4, True), ("ce+ohem", 2, False), ("ce", 4, True)])
+@pytest.mark.parametrize("lstride", [1, 2])
+def test_seg_loss_vs_oracle(loss_str, ncls, post, lstride):
+    from oracle import functional as OF
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    logits = (torch.randn(2, ncls, 16, 24, generator=g) * 2).cuda().requires_grad_(True)
+    hi = 5 if post else 2
+    labels = torch.randint(0, hi, (2, 16 * lstride, 24 * lstride), generator=g, dtype=torch.uint8).cuda()
+    loss = ops.seg_loss(logits, labels, loss_str, post, weight=0.5, lstride=lstride)
+    loss.backward()
+    lr = logits.detach().cpu().clone().requires_grad_(True)
+    ref = 0.5 * OF.loss_forward(lr, labels.cpu()[:, ::lstride, ::lstride], loss_str, post)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert rel(logits.grad, lr.grad) < 1e-4
+
+
+def test_f1_and_postprocess_bit_exact():
+    from oracle import functional as OF
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    # localisation metric (2 classes)
+    logits = torch.randn(2, 2, 32, 32, generator=g)
+    logits[0, :, 0, :4] = 1.25  # exact ties -> class 0
+    labels = torch.randint(0, 2, (2, 32, 32), generator=g, dtype=torch.uint8)
+    ctr = torch.zeros(3, dtype=torch.int64, device="cuda")
+    pred = torch.empty((2, 32, 32), dtype=torch.uint8, device="cuda")
+    ops.f1_update(logits.cuda(), labels.cuda(), 2, ctr, pred)
+    tp, fp, fn = OF.f1_counters(logits, labels, 2)
+    assert ctr.cpu().tolist() == [int(tp[0]), int(fp[0]), int(fn[0])]
+    assert torch.equal(pred.cpu(), torch.argmax(logits, 1).to(torch.uint8))
+    # damage metric (5 classes, 4 logits, building pixels only)
+    logits4 = torch.randn(2, 4, 32, 32, generator=g)
+    labels5 = torch.randint(0, 5, (2, 32, 32), generator=g, dtype=torch.uint8)
+    ctr4 = torch.zeros(12, dtype=torch.int64, device="cuda")
+    ops.f1_update(logits4.cuda(), labels5.cuda(), 5, ctr4)
+    tp, fp, fn = OF.f1_counters(logits4, labels5, 5)
+    assert ctr4.cpu().tolist() == [*map(int, tp), *map(int, fp), *map(int, fn)]
+    # post-process from probabilities: bit-exact against the numpy rule
+    loc = torch.rand(64, 64, generator=g)
+    dmg = torch.softmax(torch.randn(4, 64, 64, generator=g), 0)
+    dmg[:, 0, :8] = 0.25
+    pre, post = ops.post_process_probs(loc.cuda(), dmg.cuda())
+    pre_r, post_r = OF.post_process(loc.numpy(), dmg.numpy())
+    assert np.array_equal(pre.cpu().numpy(), pre_r) and np.array_equal(post.cpu().numpy(), post_r)
+    # fused from logits: identical away from the two thresholds
+    loc_l = torch.randn(1, 2, 64, 64, generator=g) * 3
+    dmg_l = torch.randn(1, 4, 64, 64, generator=g)
+    pre2, post2 = ops.post_process(loc_l.cuda(), dmg_l.cuda())
+    prob = torch.sigmoid(loc_l[0, 1])
+    safe = ((prob - 0.3).abs() > 1e-5) & ((prob - 0.1).abs() > 1e-5)
+    pre_r2, post_r2 = OF.post_process(prob.numpy(), torch.softmax(dmg_l[0], 0).numpy())
+    assert np.array_equal(pre2[0].cpu().numpy()[safe.numpy()], pre_r2[safe.numpy()])
+    assert np.array_equal(post2[0].cpu().numpy()[safe.numpy()], post_r2[safe.numpy()])
+
+
+def test_mean4_and_normalize_and_adamw():
+    from oracle import functional as OF
+    ops = _ops()
+    ts = [rnd(2, 2, 8, 8, seed=i) for i in range(4)]
+    m = ops.mean4(*ts)
+    ref = ts[0].clone()
+    for t in ts[1:]:
+        ref += t
+    ref /= 4
+    assert torch.equal(m, ref.contiguous(memory_format=CL))
+    g = torch.Generator().manual_seed(1)
+    pre = torch.randint(0, 256, (2, 16, 16, 3), generator=g, dtype=torch.uint8)
+    post = torch.randint(0, 256, (2, 16, 16, 3), generator=g, dtype=torch.uint8)
+    out = ops.normalize_tiles(pre.cuda(), post.cuda(), torch.float32)
+    ref = np.stack([np.concatenate([OF.normalize_tile(pre[i].numpy()), OF.normalize_tile(post[i].numpy())], 0) for i in range(2)])
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-6
+    out3 = ops.normalize_tiles(pre.cuda(), None, torch.bfloat16)
+    assert out3.shape == (2, 3, 16, 16) and out3.dtype == torch.bfloat16
+    # AdamW against torch.optim.AdamW
+    p = rnd(1000, seed=1)
+    pr = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([pr], lr=3e-4, weight_decay=0.01)
+    m_, v_ = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        gq = rnd(1000, seed=10 + step)
+        pr.grad = gq.clone()
+        opt.step()
+        ops.adamw_step(p, gq, m_, v_, 3e-4, 0.9, 0.999, 1e-8, 0.01, step)
+    assert rel(p, pr.data) < 1e-5

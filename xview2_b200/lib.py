@@ -1,0 +1,156 @@
+"""ctypes binding of libxv2.so -- the C ABI declared in include/xv2.h.
+
+The library is mandatory: importing this module (or calling any op) without the built extension raises.  There is no
+CPU or PyTorch fallback behind these calls.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_double, c_float, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxv2.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+LOSS_DICE, LOSS_FOCAL, LOSS_CE = 1, 2, 4
+E_UNSUPPORTED = -3
+
+
+class ConvGeom(ctypes.Structure):
+    _fields_ = [(n, c_int32) for n in ("n", "h", "w", "c", "oh", "ow", "k", "r", "s", "stride", "pad", "dil", "ups",
+                                        "groups", "dtype", "out_dtype")]
+
+
+class TcConv(ctypes.Structure):
+    _fields_ = [(n, c_int32) for n in ("n", "h", "w", "c0", "c1", "ld0", "ld1", "k", "r", "s", "pad", "dil", "groups",
+                                        "convt", "out_dtype", "ldo")]
+
+
+P, I32, I64, F, D = c_void_p, c_int32, c_int64, c_float, c_double
+
+_SIGNATURES = {
+    "xv2_version": [],
+    "xv2_init": [I32],
+    "xv2_conv_gather_simt": [POINTER(ConvGeom), P, P, P, P, P],
+    "xv2_conv_wgrad_simt": [POINTER(ConvGeom), P, P, P, P],
+    "xv2_colsum": [P, I64, I32, I32, P, P],
+    "xv2_pack_weight": [P, P, I32, I32, I32, I32, I32, I32, I32, P],
+    "xv2_conv_tc": [POINTER(TcConv), P, P, P, P, P, P, P],
+    "xv2_wgrad_tc": [POINTER(TcConv), P, P, P, I32, P, P],
+    "xv2_bn_stats": [P, I64, I32, I32, P, P],
+    "xv2_bn_finalize": [P, I64, I32, P, P, P, P, F, F, P, P, P, P, P],
+    "xv2_bn_eval_coeffs": [I32, P, P, P, P, F, P, P, P],
+    "xv2_bn_apply": [P, P, P, I64, I32, I32, P, P, I32, P],
+    "xv2_bn_bwd_reduce": [P, P, P, I64, I32, I32, P, P, P, P, I32, P, P],
+    "xv2_bn_bwd_apply": [P, P, P, P, P, I64, I32, I32, P, P, P, P, P, I32, P, I64, P, P, P],
+    "xv2_maxpool_fwd": [P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
+    "xv2_maxpool_bwd": [P, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
+    "xv2_avgpool_fwd": [P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
+    "xv2_avgpool_bwd": [P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
+    "xv2_splat_gap": [P, P, I32, I64, I32, I32, P],
+    "xv2_rsoftmax_fwd": [P, P, I32, I32, P],
+    "xv2_rsoftmax_bwd": [P, P, P, I32, I32, P],
+    "xv2_splat_combine": [P, P, P, I32, I64, I32, I32, P],
+    "xv2_splat_bwd_att": [P, P, P, I32, I64, I32, I32, P],
+    "xv2_splat_bwd_x": [P, P, P, P, I32, I64, I32, I32, P],
+    "xv2_add_act": [P, P, P, I64, I32, I32, P],
+    "xv2_act_bwd": [P, P, P, I64, I32, I32, P],
+    "xv2_gate_fwd": [P, P, P, I64, I32, I32, P],
+    "xv2_gate_bwd": [P, P, P, P, P, I64, I32, I32, P],
+    "xv2_flip": [P, P, I32, I32, I32, I32, I32, I32, I32, P],
+    "xv2_cast": [P, I32, P, I32, I64, P],
+    "xv2_loss_partials": [P, P, I32, I32, I32, I32, I32, I32, P, P],
+    "xv2_loss_finalize": [P, I32, I32, F, P, P, P],
+    "xv2_loss_backward": [P, P, I32, I32, I32, I32, I32, I32, I32, P, P, P, P],
+    "xv2_f1_update": [P, P, I64, I32, P, P, P],
+    "xv2_mean4": [P, P, P, P, P, I64, P],
+    "xv2_post_process": [P, P, I64, P, P, P],
+    "xv2_post_process_probs": [P, P, I64, P, P, P],
+    "xv2_head_fwd": [P, P, P, P, I64, I32, I32, I32, P],
+    "xv2_head_bwd": [P, P, P, P, P, P, I64, I32, I32, I32, P],
+    "xv2_normalize_tiles": [P, P, P, I32, I32, I32, I32, P],
+    "xv2_adamw": [P, P, P, P, I64, F, F, F, F, F, I32, P],
+}
+
+_lib = None
+_launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+class Xv2Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libxv2.so; raises if the extension has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Xv2Error(f"{LIB_PATH} is missing: build it with `python -m xview2_b200.build` "
+                       "(the CUDA extension is mandatory, there is no CPU/PyTorch fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.xv2_last_error.restype = ctypes.c_char_p
+    lib.xv2_last_error.argtypes = []
+    for name, sig in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+        fn.restype = c_int32
+        fn.argtypes = sig
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return ["xv2_last_error"] + list(_SIGNATURES)
+
+
+def last_error():
+    return load().xv2_last_error().decode()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise Xv2Error(f"unsupported activation dtype {t.dtype}")
+
+
+def call(name, *args, allow_unsupported=False):
+    """Calls an entry point with the current stream appended; raises Xv2Error on failure."""
+    global _launches
+    lib = load()
+    rc = getattr(lib, name)(*args, stream_ptr())
+    if rc == 0:
+        _launches += 1
+        return 0
+    if rc == E_UNSUPPORTED and allow_unsupported:
+        return rc
+    raise Xv2Error(f"{name} failed ({rc}): {lib.xv2_last_error().decode()}")
+
+
+def launches():
+    return _launches
+
+
+_initialised = set()
+
+
+def init(device=None):
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if dev in _initialised:
+        return
+    lib = load()
+    rc = lib.xv2_init(dev)
+    if rc != 0:
+        raise Xv2Error(f"xv2_init({dev}) failed ({rc}): {lib.xv2_last_error().decode()}")
+    _initialised.add(dev)

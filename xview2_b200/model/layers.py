@@ -1,0 +1,158 @@
+"""Decoder / head building blocks with the reference's class names, constructor signatures and parameter names
+(/root/reference/model/layers.py) so checkpoints load strictly -- but every forward pass runs libxv2 kernels.
+
+The torch.nn layers created here are PARAMETER CONTAINERS only (they define state_dict keys and initialisation);
+their own forward() is never called.
+"""
+import torch
+from torch import nn
+
+from .. import ops
+from ..lib import ACT_LRELU, ACT_NONE, ACT_RELU
+
+
+def _cl(module):
+    """Keeps 4-D weights physically channels-last ([K][R][S][C]) so kernels and gradients share one layout."""
+    for p in module.parameters(recurse=False):
+        if p.dim() == 4:
+            p.data = p.data.contiguous(memory_format=torch.channels_last)
+    return module
+
+
+def conv_param(cin, cout, k, stride=1, padding=0, dilation=1, groups=1, bias=False):
+    return _cl(nn.Conv2d(cin, cout, k, stride, padding, dilation, groups, bias))
+
+
+def run_conv(conv, x, x2=None):
+    """Runs the nn.Conv2d parameter container `conv` through the xv2 convolution (optionally on cat(x, x2))."""
+    return ops.conv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0], conv.groups, x2)
+
+
+class ConvLayer(nn.Module):
+    """3x3 conv (no bias) -> BatchNorm -> LeakyReLU(0.01).  layers.py:89-100"""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = conv_param(in_channels, out_channels, 3, padding=1)
+        self.batch_norm = nn.BatchNorm2d(out_channels, affine=True)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.01, inplace=True)  # kept for module-tree parity (no parameters)
+
+    def forward(self, inputs, second=None):
+        """`second`: optional tensor concatenated after `inputs` on channels without materialising the cat."""
+        return ops.batch_norm_act(run_conv(self.conv, inputs, second), self.batch_norm, ACT_LRELU)
+
+
+class ConvBlock(nn.Module):
+    """layers.py:119-128"""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv1 = ConvLayer(in_channels, out_channels)
+        self.conv2 = ConvLayer(out_channels, out_channels)
+
+    def forward(self, inputs, second=None):
+        return self.conv2(self.conv1(inputs, second))
+
+
+class AttentionLayer(nn.Module):
+    """1x1 conv (no bias) -> BatchNorm.  layers.py:68-77"""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = conv_param(in_channels, out_channels, 1)
+        self.batch_norm = nn.BatchNorm2d(out_channels, affine=True)
+
+    def forward(self, inputs, act=ACT_NONE, residual=None):
+        return ops.batch_norm_act(run_conv(self.conv, inputs), self.batch_norm, act, residual)
+
+
+class ConvTranspose(nn.Module):
+    """2x2 stride-2 transposed conv, no bias.  layers.py:80-86"""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = _cl(nn.ConvTranspose2d(in_channels, out_channels, kernel_size=2, stride=2, bias=False))
+
+    def forward(self, inputs):
+        return ops.conv_transpose2x2(inputs, self.conv.weight)
+
+
+class UpsampleBlock(nn.Module):
+    """Decoder stage: up-sample -> [attention gate] -> cat(skip) -> ConvBlock.  layers.py:131-168
+
+    The cat is never materialised: the first 3x3 conv reads (up, skip) as two sources.
+    """
+
+    def __init__(self, in_channels, out_channels, skip_channels, attention, dec_interp):
+        super().__init__()
+        if dec_interp:
+            raise NotImplementedError("--dec_interp (bilinear decoder, layers.py:154) is outside the accelerated path")
+        self.attention = attention
+        self.dec_interp = dec_interp
+        self.skip_channels = skip_channels
+        self.conv_tranpose = ConvTranspose(in_channels, out_channels)  # (sic) the reference's attribute name
+        self.conv_block = ConvBlock(skip_channels + out_channels, out_channels)
+        if skip_channels > 0 and attention:
+            att = out_channels // 2
+            self.conv_o = AttentionLayer(out_channels, att)
+            self.conv_s = AttentionLayer(skip_channels, att)
+            self.psi = AttentionLayer(att, 1)
+            self.sigmoid = nn.Sigmoid()
+            self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, inputs, skip):
+        out = self.conv_tranpose(inputs)
+        if self.skip_channels == 0:
+            return self.conv_block(out)
+        if self.attention:
+            # relu(conv_o(out) + conv_s(skip)): the add + relu ride on conv_s's BN apply pass
+            mix = self.conv_s(skip, ACT_RELU, residual=self.conv_o(out))
+            skip = ops.gate(skip, self.psi(mix))
+        return self.conv_block(out, skip)
+
+
+class FusionBlock(nn.Module):
+    """layers.py:103-116: run the pre/post stage, then two ConvLayer(2C -> C) on cat(pre, post) (cat not materialised)."""
+
+    def __init__(self, pre_conv, post_conv, channels):
+        super().__init__()
+        self.pre_conv = pre_conv
+        self.post_conv = post_conv
+        self.conv_pre = ConvLayer(2 * channels, channels)
+        self.conv_post = ConvLayer(2 * channels, channels)
+
+    def forward(self, pre, post, dec_pre=None, dec_post=None, last_dec=False):
+        pre = self.pre_conv(pre, dec_pre) if dec_pre is not None or last_dec else self.pre_conv(pre)
+        post = self.post_conv(post, dec_post) if dec_post is not None or last_dec else self.post_conv(post)
+        return self.conv_pre(pre, post), self.conv_post(pre, post)
+
+
+class OutputBlock(nn.Module):
+    """1x1 conv + bias to n_class logits (fp32).  layers.py:171-189"""
+
+    def __init__(self, in_channels, nclass, interpolate):
+        super().__init__()
+        if interpolate:
+            raise NotImplementedError("--interpolate head (layers.py:186-188) is outside the accelerated path")
+        if nclass == 3:
+            raise NotImplementedError("coral head (layers.py:175-178) is outside the accelerated path")
+        self.interpolate = interpolate
+        self.coral_loss = False
+        self.conv = nn.Conv2d(in_channels, nclass, kernel_size=1)
+
+    def forward(self, inputs, second=None):
+        if second is not None:  # Siamese / fused heads read cat(pre, post): tiny-N GEMM, concatenate then stream once
+            inputs = torch.cat((inputs, second), 1)
+        return ops.head(inputs, self.conv.weight, self.conv.bias)
+
+
+class PPM(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        raise NotImplementedError("--ppm (layers.py:6-29) is outside the accelerated path (SURVEY.md 8f item 4)")
+
+
+class ASPP(nn.Module):
+    def __init__(self, in_channels, dilation):
+        super().__init__()
+        raise NotImplementedError("--aspp (layers.py:32-65) is outside the accelerated path (SURVEY.md 8f item 4)")

@@ -1,0 +1,736 @@
+"""Differentiable operators of the segmentation hot path, each a thin torch.autograd.Function over libxv2 entry points.
+
+Tensors are logical NCHW with channels-last strides (physical NHWC), bf16 (tensor-core path) or fp32 (parity path).
+PyTorch supplies device memory, streams and the autograd tape; every arithmetic kernel is ours (xview2_b200/csrc).
+"""
+import torch
+
+from . import lib
+from .lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32, ConvGeom, TcConv, call, dtype_code, ptr
+
+CL = torch.channels_last
+
+# Set to False to force the SIMT path everywhere (used by tests to cross-check the tensor-core kernels).
+USE_TENSOR_CORES = True
+
+
+def nhwc(t):
+    """Returns `t` with channels-last strides (no copy if it already has them)."""
+    if t.dim() != 4:
+        raise lib.Xv2Error(f"expected a 4-D activation, got shape {tuple(t.shape)}")
+    if t.is_contiguous(memory_format=CL):
+        # size-1 dims make the check ambiguous; normalise strides so data_ptr arithmetic is NHWC for sure
+        n, c, h, w = t.shape
+        if t.stride() == (h * w * c, 1, w * c, c):
+            return t
+        return t.as_strided((n, c, h, w), (h * w * c, 1, w * c, c))
+    return t.contiguous(memory_format=CL)
+
+
+def empty_act(n, c, h, w, dtype, device):
+    return torch.empty((n, c, h, w), dtype=dtype, device=device, memory_format=CL)
+
+
+def _require_cuda(t):
+    if not t.is_cuda:
+        raise lib.Xv2Error("xview2_b200 operators run on CUDA tensors only (no CPU fallback)")
+    lib.init(t.device.index)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# packed weights (bf16 / fp32 copies in kernel order), cached per parameter version
+# ---------------------------------------------------------------------------------------------------------------
+_pack_cache = {}
+
+
+def _weight_phys(weight):
+    """fp32 parameter in its physical channels-last order [A][R][S][B]; converts once if needed."""
+    if weight.dtype != torch.float32:
+        raise lib.Xv2Error("master weights must be fp32")
+    return nhwc(weight)
+
+
+def pack_weight(weight, mode, dtype, groups=1):
+    """mode 0: [K][R][S][Cg]; mode 1: dgrad order; mode 2: transposed-conv GEMM rows.  Cached until the parameter changes."""
+    w = _weight_phys(weight)
+    key = (weight.data_ptr(), mode, dtype, groups)
+    ver = weight._version
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == ver and hit[1].device == weight.device:
+        return hit[1]
+    a, b, r, s = w.shape
+    out = torch.empty(w.numel(), dtype=dtype, device=w.device)
+    call("xv2_pack_weight", ptr(w), ptr(out), a, r, s, b, groups, mode, dtype_code(out))
+    _pack_cache[key] = (ver, out)
+    return out
+
+
+def clear_weight_cache():
+    _pack_cache.clear()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# convolution
+# ---------------------------------------------------------------------------------------------------------------
+def _out_size(i, k, stride, pad, dil):
+    return (i + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def _tc_ok(x):
+    return USE_TENSOR_CORES and x.dtype == torch.bfloat16
+
+
+def _conv_gather(src, wpacked, bias, n, h, w, c, oh, ow, k, r, s, stride, pad, dil, ups, groups, out_dtype):
+    out = empty_act(n, k, oh, ow, out_dtype, src.device)
+    g = ConvGeom(n, h, w, c, oh, ow, k, r, s, stride, pad, dil, ups, groups, dtype_code(src),
+                 F32 if out_dtype == torch.float32 else BF16)
+    call("xv2_conv_gather_simt", g, ptr(src), ptr(wpacked), ptr(bias), ptr(out))
+    return out
+
+
+class _Conv2d(torch.autograd.Function):
+    """nn.Conv2d (layers.py:92,71; encoder convs unet.py:52) with an optional second source concatenated on channels."""
+
+    @staticmethod
+    def forward(ctx, x, x2, weight, bias, stride, pad, dil, groups):
+        _require_cuda(x)
+        x = nhwc(x)
+        n, c0, h, w = x.shape
+        c1 = 0
+        if x2 is not None:
+            x2 = nhwc(x2)
+            c1 = x2.shape[1]
+        k, cg, r, s = weight.shape
+        assert (c0 + c1) == cg * groups, "channel mismatch"
+        oh, ow = _out_size(h, r, stride, pad, dil), _out_size(w, s, stride, pad, dil)
+        ctx.cfg = (stride, pad, dil, groups, c0, c1)
+        ctx.save_for_backward(x, x2, weight)
+        ctx.has_bias = bias is not None
+        use_tc = _tc_ok(x) and stride == 1 and oh == h and ow == w
+        if use_tc:
+            wp = pack_weight(weight, 0, torch.bfloat16, groups)
+            out = empty_act(n, k, h, w, x.dtype, x.device)
+            p = TcConv(n, h, w, c0, c1, 0, 0, k, r, s, pad, dil, groups, 0, BF16, 0)
+            rc = call("xv2_conv_tc", p, ptr(x), ptr(x2), ptr(wp), ptr(bias), ptr(out), None, allow_unsupported=True)
+            if rc == 0:
+                return out
+        src = x if x2 is None else torch.cat((x, x2), 1)  # SIMT path only: plumbing copy
+        src = nhwc(src)
+        wp = pack_weight(weight, 0, x.dtype, groups)
+        return _conv_gather(src, wp, bias, n, h, w, c0 + c1, oh, ow, k, r, s, stride, pad, dil, 1, groups, x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, x2, weight = ctx.saved_tensors
+        stride, pad, dil, groups, c0, c1 = ctx.cfg
+        dy = nhwc(dy)
+        n, _, h, w = x.shape
+        k, cg, r, s = weight.shape
+        oh, ow = dy.shape[2], dy.shape[3]
+        dx = dx2 = dw = db = None
+        same = stride == 1 and oh == h and ow == w
+        tc = _tc_ok(x) and same
+        need_dx = ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1])
+        if need_dx:
+            pad_t = dil * (r - 1) - pad
+            done = False
+            if tc:
+                wt = pack_weight(weight, 1, torch.bfloat16, groups).view(c0 + c1, -1)
+                outs = []
+                ok = True
+                for lo, cc in ((0, c0), (c0, c1)):
+                    if cc == 0:
+                        outs.append(None)
+                        continue
+                    if groups > 1:
+                        wsub, kk, gg = wt, k, groups
+                    else:
+                        wsub, kk, gg = wt[lo:lo + cc], k, 1
+                    o = empty_act(n, cc, h, w, x.dtype, x.device)
+                    p = TcConv(n, h, w, kk, 0, 0, 0, cc, r, s, pad_t, dil, gg, 0, BF16, 0)
+                    rc = call("xv2_conv_tc", p, ptr(dy), None, ptr(wsub), None, ptr(o), None, allow_unsupported=True)
+                    if rc != 0:
+                        ok = False
+                        break
+                    outs.append(o)
+                if ok:
+                    dx, dx2 = outs
+                    done = True
+            if not done:
+                wt = pack_weight(weight, 1, x.dtype, groups)
+                full = _conv_gather(dy, wt, None, n, oh, ow, k, h, w, c0 + c1, r, s, 1, pad_t, dil, stride, groups, x.dtype)
+                if x2 is None:
+                    dx = full
+                else:
+                    dx, dx2 = nhwc(full[:, :c0]), nhwc(full[:, c0:])
+        if ctx.needs_input_grad[2]:
+            dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device).contiguous(memory_format=CL)
+            done = False
+            if tc:
+                p = TcConv(n, h, w, c0, c1, 0, 0, k, r, s, pad, dil, groups, 0, BF16, 0)
+                rc = call("xv2_wgrad_tc", p, ptr(x), ptr(x2), ptr(dy), 0, ptr(dw), allow_unsupported=True)
+                done = rc == 0
+            if not done:
+                src = x if x2 is None else nhwc(torch.cat((x, x2), 1))
+                g = ConvGeom(n, h, w, c0 + c1, oh, ow, k, r, s, stride, pad, dil, 1, groups, dtype_code(x), F32)
+                call("xv2_conv_wgrad_simt", g, ptr(src), ptr(dy), ptr(dw))
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = torch.zeros(k, dtype=torch.float32, device=x.device)
+            _colsum(dy, db)
+        return dx, dx2, dw, db, None, None, None, None
+
+
+def _colsum(t, out):
+    n, k, h, w = t.shape
+    if k <= 256:
+        call("xv2_colsum", ptr(t), n * h * w, k, dtype_code(t), ptr(out))
+    else:
+        stats = torch.zeros(2 * k, dtype=torch.float64, device=t.device)
+        call("xv2_bn_stats", ptr(t), n * h * w, k, dtype_code(t), ptr(stats))
+        out.copy_(stats[:k])
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, x2=None):
+    return _Conv2d.apply(x, x2, weight, bias, stride, padding, dilation, groups)
+
+
+class _ConvT2x2(torch.autograd.Function):
+    """nn.ConvTranspose2d(k=2, s=2, bias=False) (layers.py:83) as GEMM + pixel-shuffle store."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        _require_cuda(x)
+        x = nhwc(x)
+        n, cin, h, w = x.shape
+        cout = weight.shape[1]
+        assert weight.shape[0] == cin and weight.shape[2:] == (2, 2)
+        ctx.save_for_backward(x, weight)
+        if _tc_ok(x):
+            wp = pack_weight(weight, 2, torch.bfloat16)
+            out = empty_act(n, cout, 2 * h, 2 * w, x.dtype, x.device)
+            p = TcConv(n, h, w, cin, 0, 0, 0, cout, 1, 1, 0, 1, 1, 1, BF16, 0)
+            rc = call("xv2_conv_tc", p, ptr(x), None, ptr(wp), None, ptr(out), None, allow_unsupported=True)
+            if rc == 0:
+                return out
+        wp = pack_weight(weight, 1, x.dtype)  # [cout][1-kh][1-kw][cin]
+        return _conv_gather(x, wp, None, n, h, w, cin, 2 * h, 2 * w, cout, 2, 2, 1, 1, 1, 2, 1, x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = nhwc(dy)
+        n, cin, h, w = x.shape
+        cout = weight.shape[1]
+        dx = dw = None
+        tc = _tc_ok(x)
+        if ctx.needs_input_grad[0]:
+            done = False
+            if tc:
+                wp = pack_weight(weight, 0, torch.bfloat16)  # physical [cin][kh][kw][cout] is already the GEMM order
+                dx = empty_act(n, cin, h, w, x.dtype, x.device)
+                p = TcConv(n, h, w, cout, 0, 0, 0, cin, 2, 2, 0, 1, 1, 2, BF16, 0)
+                rc = call("xv2_conv_tc", p, ptr(dy), None, ptr(wp), None, ptr(dx), None, allow_unsupported=True)
+                done = rc == 0
+            if not done:
+                wp = pack_weight(weight, 0, x.dtype)
+                dx = _conv_gather(dy, wp, None, n, 2 * h, 2 * w, cout, h, w, cin, 2, 2, 2, 0, 1, 1, 1, x.dtype)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device).contiguous(memory_format=CL)
+            done = False
+            if tc:
+                p = TcConv(n, h, w, cin, 0, 0, 0, cout, 2, 2, 0, 1, 1, 1, BF16, 0)
+                rc = call("xv2_wgrad_tc", p, ptr(x), None, ptr(dy), 0, ptr(dw), allow_unsupported=True)
+                done = rc == 0
+            if not done:
+                # gradient of the stride-2 conv whose "input" is dy and "output" is x: dw[cin][kh][kw][cout]
+                g = ConvGeom(n, 2 * h, 2 * w, cout, h, w, cin, 2, 2, 2, 0, 1, 1, 1, dtype_code(x), F32)
+                call("xv2_conv_wgrad_simt", g, ptr(dy), ptr(x), ptr(dw))
+        return dx, dw
+
+
+def conv_transpose2x2(x, weight):
+    return _ConvT2x2.apply(x, weight)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# batch norm (+ activation, + residual)
+# ---------------------------------------------------------------------------------------------------------------
+class _BatchNormAct(torch.autograd.Function):
+    """nn.BatchNorm2d [+ residual add] [+ ReLU / LeakyReLU(0.01)] in one apply pass (layers.py:93-94, unet.py:52)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, training, momentum, eps, act):
+        _require_cuda(x)
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        pixels = n * h * w
+        dev = x.device
+        if residual is not None:
+            residual = nhwc(residual)
+        coef = torch.empty(4, c, dtype=torch.float32, device=dev)  # mean, invstd, scale, shift
+        mean, invstd, scale, shift = coef[0], coef[1], coef[2], coef[3]
+        if training:
+            if pixels <= 1:
+                raise ValueError("Expected more than 1 value per channel when training")  # torch's own BN check
+            stats = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+            call("xv2_bn_stats", ptr(x), pixels, c, dtype_code(x), ptr(stats))
+            call("xv2_bn_finalize", ptr(stats), pixels, c, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                 float(momentum), float(eps), ptr(mean), ptr(invstd), ptr(scale), ptr(shift))
+        else:
+            mean.copy_(running_mean)
+            invstd.copy_(torch.rsqrt(running_var + eps))
+            call("xv2_bn_eval_coeffs", c, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), float(eps),
+                 ptr(scale), ptr(shift))
+        y = torch.empty_like(x)
+        call("xv2_bn_apply", ptr(x), ptr(residual), ptr(y), pixels, c, dtype_code(x), ptr(scale), ptr(shift), act)
+        ctx.save_for_backward(x, residual, gamma, coef)
+        ctx.cfg = (training, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, residual, gamma, coef = ctx.saved_tensors
+        training, act = ctx.cfg
+        dy = nhwc(dy)
+        n, c, h, w = x.shape
+        pixels = n * h * w
+        mean, invstd, scale, shift = coef[0], coef[1], coef[2], coef[3]
+        dt = dtype_code(x)
+        red = torch.zeros(2 * c, dtype=torch.float64, device=x.device)
+        call("xv2_bn_bwd_reduce", ptr(dy), ptr(x), ptr(residual), pixels, c, dt, ptr(scale), ptr(shift), ptr(mean),
+             ptr(invstd), act, ptr(red))
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if residual is not None and ctx.needs_input_grad[1] else None
+        dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)
+        call("xv2_bn_bwd_apply", ptr(dy), ptr(x), ptr(residual), ptr(dx), ptr(dres), pixels, c, dt, ptr(scale),
+             ptr(shift), ptr(mean), ptr(invstd), ptr(gamma), act, ptr(red) if training else None, pixels,
+             ptr(dgb[0]) if training else None, ptr(dgb[1]) if training else None)
+        if not training:
+            dgb[1].copy_(red[:c])
+            dgb[0].copy_(red[c:])
+        return dx, dres, dgb[0], dgb[1], None, None, None, None, None, None
+
+
+def batch_norm_act(x, bn, act=ACT_NONE, residual=None):
+    """Applies the nn.BatchNorm2d module `bn` (its parameters / buffers / training flag) followed by `act`."""
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    use_batch = bn.training or not bn.track_running_stats
+    return _BatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch,
+                               bn.momentum if bn.momentum is not None else 0.1, bn.eps, act)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pooling
+# ---------------------------------------------------------------------------------------------------------------
+def _pool_out(i, k, s, p, ceil_mode):
+    if ceil_mode:
+        o = -(-(i + 2 * p - k) // s) + 1
+        if (o - 1) * s >= i + p:
+            o -= 1
+        return o
+    return (i + 2 * p - k) // s + 1
+
+
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        _require_cuda(x)
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        oh, ow = _pool_out(h, k, stride, pad, False), _pool_out(w, k, stride, pad, False)
+        y = empty_act(n, c, oh, ow, x.dtype, x.device)
+        call("xv2_maxpool_fwd", ptr(x), ptr(y), n, h, w, c, oh, ow, k, stride, pad, dtype_code(x))
+        ctx.save_for_backward(x)
+        ctx.cfg = (k, stride, pad, oh, ow)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        k, stride, pad, oh, ow = ctx.cfg
+        dy = nhwc(dy)
+        n, c, h, w = x.shape
+        dx = torch.empty_like(x)
+        call("xv2_maxpool_bwd", ptr(x), ptr(dy), ptr(dx), n, h, w, c, oh, ow, k, stride, pad, dtype_code(x))
+        return dx, None, None, None
+
+
+class _AvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad, ceil_mode, count_include_pad):
+        _require_cuda(x)
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        oh, ow = _pool_out(h, k, stride, pad, ceil_mode), _pool_out(w, k, stride, pad, ceil_mode)
+        y = empty_act(n, c, oh, ow, x.dtype, x.device)
+        call("xv2_avgpool_fwd", ptr(x), ptr(y), n, h, w, c, oh, ow, k, stride, pad, int(count_include_pad), dtype_code(x))
+        ctx.cfg = (k, stride, pad, int(count_include_pad), n, c, h, w, oh, ow)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        k, stride, pad, cip, n, c, h, w, oh, ow = ctx.cfg
+        dy = nhwc(dy)
+        dx = empty_act(n, c, h, w, dy.dtype, dy.device)
+        call("xv2_avgpool_bwd", ptr(dy), ptr(dx), n, h, w, c, oh, ow, k, stride, pad, cip, dtype_code(dy))
+        return dx, None, None, None, None, None
+
+
+def max_pool2d(x, k, stride, pad):
+    return _MaxPool.apply(x, k, stride, pad)
+
+
+def avg_pool2d(x, k, stride, pad=0, ceil_mode=False, count_include_pad=True):
+    if k == 1 and stride == 1:
+        return x
+    return _AvgPool.apply(x, k, stride, pad, ceil_mode, count_include_pad)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# split attention (ResNeSt SplAtConv2d tail: radix-sum -> GAP -> fc1 -> bn1 -> relu -> fc2 -> r-softmax -> combine)
+# ---------------------------------------------------------------------------------------------------------------
+def _fc(x2d, w2d, bias):
+    """[n][c] x [k][c]^T + bias -> [n][k], fp32, through the SIMT gather conv on a 1x1 'image'."""
+    n, c = x2d.shape
+    k = w2d.shape[0]
+    out = torch.empty((n, k), dtype=torch.float32, device=x2d.device)
+    g = ConvGeom(n, 1, 1, c, 1, 1, k, 1, 1, 1, 0, 1, 1, 1, F32, F32)
+    call("xv2_conv_gather_simt", g, ptr(x2d), ptr(w2d), ptr(bias), ptr(out))
+    return out
+
+
+def _fc_wgrad(x2d, dy2d):
+    n, c = x2d.shape
+    k = dy2d.shape[1]
+    dw = torch.zeros((k, c), dtype=torch.float32, device=x2d.device)
+    g = ConvGeom(n, 1, 1, c, 1, 1, k, 1, 1, 1, 0, 1, 1, 1, F32, F32)
+    call("xv2_conv_wgrad_simt", g, ptr(x2d), ptr(dy2d), ptr(dw))
+    db = torch.zeros(k, dtype=torch.float32, device=x2d.device)
+    if k <= 256:
+        call("xv2_colsum", ptr(dy2d), n, k, F32, ptr(db))
+    else:
+        st = torch.zeros(2 * k, dtype=torch.float64, device=x2d.device)
+        call("xv2_bn_stats", ptr(dy2d), n, k, F32, ptr(st))
+        db.copy_(st[:k])
+    return dw, db
+
+
+class _SplitAttention(torch.autograd.Function):
+    """Whole split-attention tail as one tape node so that d(x) is written in a single pass.
+
+    forward : gap = mean_hw(x0 + x1); a = r-softmax(fc2(relu(bn1(fc1(gap))))); out = a0*x0 + a1*x1
+    backward: datt = <dout, x_r>_hw  ->  tiny FC/BN chain  ->  dgap;  dx_r = a_r*dout + dgap/hw
+    The FC/BN arithmetic is fp32 on [n][c]-sized tensors and reuses the SIMT conv and BN kernels.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, gamma, beta, rmean, rvar, w2, b2, training, momentum, eps):
+        _require_cuda(x)
+        x = nhwc(x)
+        n, c2, h, w = x.shape
+        c = c2 // 2
+        inter = w1.shape[0]
+        dev = x.device
+        gap = torch.empty((n, c), dtype=torch.float32, device=dev)
+        call("xv2_splat_gap", ptr(x), ptr(gap), n, h * w, c, dtype_code(x))
+        w1m, w2m = w1.reshape(inter, c).contiguous(), w2.reshape(c2, inter).contiguous()
+        z1 = _fc(gap, w1m, b1)
+        coef = torch.empty(4, inter, dtype=torch.float32, device=dev)
+        if training:
+            if n <= 1:
+                raise ValueError("Expected more than 1 value per channel when training")
+            st = torch.zeros(2 * inter, dtype=torch.float64, device=dev)
+            call("xv2_bn_stats", ptr(z1), n, inter, F32, ptr(st))
+            call("xv2_bn_finalize", ptr(st), n, inter, ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), float(momentum),
+                 float(eps), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]))
+        else:
+            coef[0].copy_(rmean)
+            coef[1].copy_(torch.rsqrt(rvar + eps))
+            call("xv2_bn_eval_coeffs", inter, ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), float(eps), ptr(coef[2]),
+                 ptr(coef[3]))
+        a1 = torch.empty_like(z1)
+        call("xv2_bn_apply", ptr(z1), None, ptr(a1), n, inter, F32, ptr(coef[2]), ptr(coef[3]), ACT_RELU)
+        z2 = _fc(a1, w2m, b2)
+        att = torch.empty_like(z2)
+        call("xv2_rsoftmax_fwd", ptr(z2), ptr(att), n, c)
+        out = empty_act(n, c, h, w, x.dtype, dev)
+        call("xv2_splat_combine", ptr(x), ptr(att), ptr(out), n, h * w, c, dtype_code(x))
+        ctx.save_for_backward(x, att, gap, z1, a1, coef, w1, w2, gamma)
+        ctx.training = training
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, att, gap, z1, a1, coef, w1, w2, gamma = ctx.saved_tensors
+        training = ctx.training
+        dout = nhwc(dout)
+        n, c2, h, w = x.shape
+        c = c2 // 2
+        inter = w1.shape[0]
+        dev = x.device
+        datt = torch.zeros((n, c2), dtype=torch.float32, device=dev)
+        call("xv2_splat_bwd_att", ptr(x), ptr(dout), ptr(datt), n, h * w, c, dtype_code(x))
+        dz2 = torch.empty_like(datt)
+        call("xv2_rsoftmax_bwd", ptr(att), ptr(datt), ptr(dz2), n, c)
+        dw2, db2 = _fc_wgrad(a1, dz2)
+        w2t = pack_weight(w2, 1, torch.float32).view(inter, c2)
+        da1 = _fc(dz2, w2t, None)
+        red = torch.zeros(2 * inter, dtype=torch.float64, device=dev)
+        call("xv2_bn_bwd_reduce", ptr(da1), ptr(z1), None, n, inter, F32, ptr(coef[2]), ptr(coef[3]), ptr(coef[0]),
+             ptr(coef[1]), ACT_RELU, ptr(red))
+        dz1 = torch.empty_like(z1)
+        dgb = torch.empty(2, inter, dtype=torch.float32, device=dev)
+        call("xv2_bn_bwd_apply", ptr(da1), ptr(z1), None, ptr(dz1), None, n, inter, F32, ptr(coef[2]), ptr(coef[3]),
+             ptr(coef[0]), ptr(coef[1]), ptr(gamma), ACT_RELU, ptr(red) if training else None, n,
+             ptr(dgb[0]) if training else None, ptr(dgb[1]) if training else None)
+        if not training:
+            dgb[1].copy_(red[:inter])
+            dgb[0].copy_(red[inter:])
+        dw1, db1 = _fc_wgrad(gap, dz1)
+        w1t = pack_weight(w1, 1, torch.float32).view(c, inter)
+        dgap = _fc(dz1, w1t, None)
+        dx = torch.empty_like(x)
+        call("xv2_splat_bwd_x", ptr(dout), ptr(att), ptr(dgap), ptr(dx), n, h * w, c, dtype_code(x))
+        return (dx, dw1.reshape(w1.shape), db1, dgb[0], dgb[1], None, None, dw2.reshape(w2.shape), db2, None, None, None)
+
+
+def split_attention(x, fc1, bn1, fc2):
+    """x: (n, 2c, h, w) after bn0+relu; fc1/fc2: nn.Conv2d 1x1 with bias; bn1: nn.BatchNorm2d on (n, inter, 1, 1)."""
+    if bn1.training and bn1.num_batches_tracked is not None:
+        bn1.num_batches_tracked += 1
+    return _SplitAttention.apply(x, fc1.weight, fc1.bias, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var,
+                                 fc2.weight, fc2.bias, bn1.training, bn1.momentum, bn1.eps)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# element-wise
+# ---------------------------------------------------------------------------------------------------------------
+class _AddAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, act):
+        a, b = nhwc(a), nhwc(b)
+        y = torch.empty_like(a)
+        call("xv2_add_act", ptr(a), ptr(b), ptr(y), a.numel(), dtype_code(a), act)
+        ctx.act = act
+        if act != ACT_NONE:
+            ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if ctx.act == ACT_NONE:
+            return dy, dy, None
+        (y,) = ctx.saved_tensors
+        dy = nhwc(dy)
+        dx = torch.empty_like(y)
+        call("xv2_act_bwd", ptr(dy), ptr(y), ptr(dx), y.numel(), dtype_code(y), ctx.act)
+        return dx, dx, None
+
+
+def add_act(a, b, act=ACT_NONE):
+    return _AddAct.apply(a, b, act)
+
+
+class _Gate(torch.autograd.Function):
+    """skip * sigmoid(psi)  (layers.py:165-166); psi has one channel."""
+
+    @staticmethod
+    def forward(ctx, skip, psi):
+        skip, psi = nhwc(skip), nhwc(psi)
+        n, c, h, w = skip.shape
+        out = torch.empty_like(skip)
+        call("xv2_gate_fwd", ptr(skip), ptr(psi), ptr(out), n * h * w, c, dtype_code(skip))
+        ctx.save_for_backward(skip, psi)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        skip, psi = ctx.saved_tensors
+        dout = nhwc(dout)
+        n, c, h, w = skip.shape
+        dskip, dpsi = torch.empty_like(skip), torch.empty_like(psi)
+        call("xv2_gate_bwd", ptr(dout), ptr(skip), ptr(psi), ptr(dskip), ptr(dpsi), n * h * w, c, dtype_code(skip))
+        return dskip, dpsi
+
+
+def gate(skip, psi):
+    return _Gate.apply(skip, psi)
+
+
+class _Flip(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flip_h, flip_w):
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        y = torch.empty_like(x)
+        call("xv2_flip", ptr(x), ptr(y), n, h, w, c, int(flip_h), int(flip_w), dtype_code(x))
+        ctx.cfg = (flip_h, flip_w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _Flip.apply(dy, *ctx.cfg), None, None
+
+
+def flip(x, dims):
+    return _Flip.apply(x, 2 in dims, 3 in dims)
+
+
+class _Cast(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        _require_cuda(x)
+        x = nhwc(x)
+        ctx.src_dtype = x.dtype
+        if x.dtype == dtype:
+            return x
+        y = torch.empty_like(x, dtype=dtype)
+        call("xv2_cast", ptr(x), dtype_code(x), ptr(y), dtype_code(y), x.numel())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _Cast.apply(dy, ctx.src_dtype), None
+
+
+def cast(x, dtype):
+    return _Cast.apply(x, dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# output head, loss, metric, post-process, loader
+# ---------------------------------------------------------------------------------------------------------------
+class _Head(torch.autograd.Function):
+    """1x1 conv + bias to n_class fp32 logits (layers.py:180)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda(x)
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        ncls = weight.shape[0]
+        w2 = weight.reshape(ncls, c).contiguous()
+        logits = empty_act(n, ncls, h, w, torch.float32, x.device)
+        call("xv2_head_fwd", ptr(x), ptr(w2), ptr(bias), ptr(logits), n * h * w, c, ncls, dtype_code(x))
+        ctx.save_for_backward(x, w2)
+        ctx.wshape = weight.shape
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        x, w2 = ctx.saved_tensors
+        n, c, h, w = x.shape
+        ncls = w2.shape[0]
+        dl = nhwc(dl.float())
+        dx = torch.empty_like(x)
+        dw = torch.zeros_like(w2)
+        db = torch.zeros(ncls, dtype=torch.float32, device=x.device)
+        call("xv2_head_bwd", ptr(x), ptr(w2), ptr(dl), ptr(dx), ptr(dw), ptr(db), n * h * w, c, ncls, dtype_code(x))
+        return dx, dw.reshape(ctx.wshape), db
+
+
+def head(x, weight, bias):
+    return _Head.apply(x, weight, bias)
+
+
+class _SegLoss(torch.autograd.Function):
+    """Sum of dice / focal / ce terms (loss.py:98-101) scaled by `weight`, labels sampled with stride `lstride`."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, terms, post, weight, lstride):
+        _require_cuda(logits)
+        logits = nhwc(logits.float())
+        n, ncls, h, w = logits.shape
+        labels = labels.contiguous()
+        assert labels.dtype == torch.uint8 and labels.shape == (n, h * lstride, w * lstride)
+        dev = logits.device
+        sums = torch.zeros(3 * ncls + 3, dtype=torch.float64, device=dev)
+        call("xv2_loss_partials", ptr(logits), ptr(labels), n, h, w, ncls, lstride, int(post), ptr(sums))
+        loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        coef = torch.empty(2 * ncls + 4, dtype=torch.float32, device=dev)
+        call("xv2_loss_finalize", ptr(sums), ncls, terms, float(weight), ptr(loss), ptr(coef))
+        ctx.save_for_backward(logits, labels, coef)
+        ctx.cfg = (terms, int(post), lstride)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, labels, coef = ctx.saved_tensors
+        terms, post, lstride = ctx.cfg
+        n, ncls, h, w = logits.shape
+        dl = torch.empty_like(logits)
+        up = dloss.reshape(1).float().contiguous()
+        call("xv2_loss_backward", ptr(logits), ptr(labels), n, h, w, ncls, lstride, post, terms, ptr(coef), ptr(up), ptr(dl))
+        return dl, None, None, None, None, None
+
+
+_LOSS_BITS = {"dice": lib.LOSS_DICE, "focal": lib.LOSS_FOCAL, "ce": lib.LOSS_CE, "ohem": lib.LOSS_CE}
+
+
+def seg_loss(logits, labels, loss_str, post, weight=1.0, lstride=1):
+    """Loss.forward (loss.py:85-101) for the dice / focal / ce / ohem terms.  'ce+ohem' counts CE twice like the reference."""
+    total = None
+    fused = 0
+    extra_ce = 0
+    for name in loss_str.split("+"):
+        if name not in _LOSS_BITS:
+            raise NotImplementedError(f"loss '{name}' is outside the accelerated path (dice, focal, ce, ohem)")
+        bit = _LOSS_BITS[name]
+        if fused & bit:
+            extra_ce += 1
+        fused |= bit
+    total = _SegLoss.apply(logits, labels, fused, post, weight, lstride)
+    for _ in range(extra_ce):
+        total = total + _SegLoss.apply(logits, labels, lib.LOSS_CE, post, weight, lstride)
+    return total
+
+
+def f1_update(logits, labels, n_class, counters, pred_map=None):
+    """F1.update (utils/f1.py:28-42).  counters: int64 [3*(n_class-1)] = tp | fp | fn, accumulated in place."""
+    logits = nhwc(logits.float())
+    labels = labels.contiguous()
+    n, _, h, w = logits.shape
+    call("xv2_f1_update", ptr(logits), ptr(labels), n * h * w, n_class, ptr(counters), ptr(pred_map))
+
+
+def mean4(a, b, c, d):
+    a, b, c, d = (nhwc(t.float()) for t in (a, b, c, d))
+    out = torch.empty_like(a)
+    call("xv2_mean4", ptr(a), ptr(b), ptr(c), ptr(d), ptr(out), a.numel())
+    return out
+
+
+def post_process(loc_logits, dmg_logits):
+    """Model.save + utils/post_process.py:27-38 from logits: returns (pre, post) uint8 maps (n, h, w)."""
+    loc, dmg = nhwc(loc_logits.float()), nhwc(dmg_logits.float())
+    n, _, h, w = loc.shape
+    pre = torch.empty((n, h, w), dtype=torch.uint8, device=loc.device)
+    post = torch.empty_like(pre)
+    call("xv2_post_process", ptr(loc), ptr(dmg), n * h * w, ptr(pre), ptr(post))
+    return pre, post
+
+
+def post_process_probs(loc, dmg):
+    """utils/post_process.py:27-38 from probabilities as the reference stores them: loc (h, w), dmg (4, h, w)."""
+    loc, dmg = loc.contiguous().float(), dmg.contiguous().float()
+    h, w = loc.shape
+    pre = torch.empty((h, w), dtype=torch.uint8, device=loc.device)
+    post = torch.empty_like(pre)
+    call("xv2_post_process_probs", ptr(loc), ptr(dmg), h * w, ptr(pre), ptr(post))
+    return pre, post
+
+
+def normalize_tiles(pre_u8, post_u8=None, dtype=torch.bfloat16):
+    """uint8 (n, h, w, 3) decoded tiles -> normalised (n, 3|6, h, w) channels-last activations (pytorch_loader.py:63,169-170)."""
+    n, h, w, _ = pre_u8.shape
+    lib.init(pre_u8.device.index)
+    out = empty_act(n, 3 if post_u8 is None else 6, h, w, dtype, pre_u8.device)
+    call("xv2_normalize_tiles", ptr(pre_u8.contiguous()), ptr(None if post_u8 is None else post_u8.contiguous()),
+         ptr(out), n, h, w, dtype_code(out))
+    return out
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
+    call("xv2_adamw", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+         float(weight_decay), int(step))
