@@ -241,9 +241,13 @@ int xv2_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, 
 int xv2_normalize_tiles(const uint8_t* pre, const uint8_t* post, void* out, int32_t n, int32_t h, int32_t w,
                         int32_t out_dtype, void* stream);
 
-/* Fused AdamW over one flat parameter (torch.optim.AdamW semantics, plt.py:154): step is 1-based. */
+/* Fused AdamW over one flat parameter buffer (torch.optim.AdamW semantics, plt.py:154): step is 1-based; the gradient
+ * is multiplied by grad_scale first (1/world_size after the SUM all-reduce of the data-parallel ranks). */
 int xv2_adamw(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1, float beta2,
-              float eps, float weight_decay, int32_t step, void* stream);
+              float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+/* SGD with momentum (apex FusedSGD defaults, plt.py:152): buf = momentum*buf + g (buf = g at step 1); p -= lr*buf. */
+int xv2_sgd(float* p, const float* g, float* buf, int64_t numel, float lr, float momentum, float grad_scale,
+            int32_t step, void* stream);
 
 #ifdef __cplusplus
 }

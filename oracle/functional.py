@@ -431,5 +431,7 @@ def deterministic_state(shapes, seed=1):
         else:  # conv / convT weight: He-style fan-in scaling keeps activations O(1) through 100+ layers
             fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
             t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+        if ".fc2." in key:  # SplAt attention logits: moderate like a trained net's, not a saturated hard switch
+            t = t * 0.25
         out[key] = t.to(dtype)
     return out

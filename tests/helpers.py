@@ -22,8 +22,15 @@ def load_golden(name):
 
 
 def golden_state(fx):
+    """Seeded weights + the fixture's calibrated BN running statistics (stored under canonical keys)."""
     shapes = {k: (tuple(s), _DT[d]) for k, (s, d) in fx["state_shapes"].items()}
-    return OF.deterministic_state(shapes, fx["state_seed"])
+    state = OF.deterministic_state(shapes, fx["state_seed"])
+    cal = fx.get("calibrated_running", {})
+    for k in state:
+        ck = OF.canonical_key(k)
+        if ck in cal:
+            state[k] = cal[ck].clone()
+    return state
 
 
 def golden_inputs(fx):
@@ -32,7 +39,7 @@ def golden_inputs(fx):
     ch = 3 if ns.type == "pre" else 6
     x = torch.randn(b, ch, s, s, generator=g)
     hi = 2 if ns.type == "pre" else 5
-    cells = torch.randint(0, hi, (b, s // 8, s // 8), generator=g, dtype=torch.uint8)
+    cells = torch.randint(0, hi, (b, s // 8, s // 8), generator=g, dtype=torch.uint8)  # same draw order as tools/make_golden.py
     y = cells.repeat_interleave(8, 1).repeat_interleave(8, 2).contiguous()
     return x, y
 

@@ -4,8 +4,10 @@ has no /root/reference, it consumes the committed fixtures.
 
     python tools/make_golden.py            # writes tests/golden/<case>.pt
 
-Each fixture holds: the argparse fields, input/label seeds and shapes, eval-mode logits, train-mode logits, the loss,
-per-parameter gradient digests (sum, L2 norm, 8 sampled entries) and the post-step BN running statistics digests.
+Each fixture holds: the argparse fields, input/label seeds and shapes, the calibrated BN running statistics, eval-mode
+logits, train-mode logits, the loss, per-parameter gradient digests (sum, L2 norm, 8 sampled entries) and the post-step
+BN running statistics digests -- each from the reference modules in fp32 AND in fp64 (`*64`), plus `grad_noise`: the
+reference's own fp32-vs-fp64 gradient error per parameter, the noise floor any fp32 implementation is held to.
 Weights are NOT stored: both sides regenerate them with oracle.functional.deterministic_state (crc32-seeded per key).
 """
 import argparse
@@ -23,15 +25,16 @@ from oracle.refload import load_reference  # noqa: E402
 BASE = dict(ppm=False, aspp=False, dilation=1, no_skip=False, interpolate=False, attention=False, dec_interp=False,
             deep_supervision=False, loss_str="focal+dice", encoder="resnest50", dmg_model="siamese", type="pre", tta=False)
 
+# name: (arg overrides, batch, size).  Batch 4: ResNeSt's SplAt bn1 normalises a (B, C, 1, 1) tensor, and with B = 2
+# x_hat is a sign function -- the fixture would be chaotic in fp32 (the reference's fp32 and fp64 runs differed by 3 %).
 CASES = {
-    # name: (arg overrides, batch, size)
-    "c1_resnet50_pre": (dict(encoder="resnet50"), 2, 64),
-    "c2_resnest50_pre": (dict(encoder="resnest50"), 2, 128),
-    "c2_resnest50_pre_ce_ohem": (dict(encoder="resnest50", loss_str="ce+ohem"), 2, 64),
-    "c3_resnest50_siamese": (dict(encoder="resnest50", type="post", dmg_model="siamese"), 2, 64),
-    "c3_resnest101_siamese": (dict(encoder="resnest101", type="post", dmg_model="siamese"), 2, 64),
+    "c1_resnet50_pre": (dict(encoder="resnet50"), 4, 64),
+    "c2_resnest50_pre": (dict(encoder="resnest50"), 4, 128),
+    "c2_resnest50_pre_ce_ohem": (dict(encoder="resnest50", loss_str="ce+ohem"), 4, 64),
+    "c3_resnest50_siamese": (dict(encoder="resnest50", type="post", dmg_model="siamese"), 4, 64),
+    "c3_resnest101_siamese": (dict(encoder="resnest101", type="post", dmg_model="siamese"), 4, 64),
     "c4_resnest50_fused_ds_attn": (dict(encoder="resnest50", type="post", dmg_model="fused", deep_supervision=True,
-                                        attention=True), 2, 64),
+                                        attention=True), 4, 64),
 }
 
 
@@ -58,19 +61,27 @@ def build_reference_model(ref_unet, args):
     return ref_unet.UNetLoc(args) if args.type == "pre" else ref_unet.get_dmg_unet(args)
 
 
-def run_case(ref_unet, ref_loss, name, over, batch, size):
-    args = argparse.Namespace(**{**BASE, **over})
-    model = build_reference_model(ref_unet, args)
-    shapes = {k: (tuple(v.shape), v.dtype) for k, v in model.state_dict().items()}
-    state = OF.deterministic_state(shapes)
-    model.load_state_dict(state, strict=True)
-    x, y = make_inputs(args, batch, size)
-    loss_mod = ref_loss.Loss(args)
-
-    model.eval()
+def calibrate_running_stats(model, args, xc):
+    """Gives the BN layers running statistics that match the activations they actually see (what a trained checkpoint
+    has): ONE train-mode pass of the reference model with momentum None (cumulative average: a Siamese net that runs its
+    shared U-Net on the pre and then the post image ends up with the mean of both) on the fixture's input.  With arbitrary
+    running statistics the eval-mode residual stream grows ~2x per block (logits ~1e4) and the split-attention
+    soft-max saturates, which makes the fixture chaotic: the reference's own fp32 and fp64 runs then differ by 19 %."""
+    bns = [m for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    old = [m.momentum for m in bns]
+    for m in bns:
+        m.momentum = None
+        m.num_batches_tracked.zero_()
+    model.train()
     with torch.no_grad():
-        eval_logits = model(x).clone()
+        model(xc)
+    for m, mom in zip(bns, old):
+        m.momentum = mom
+        m.num_batches_tracked.zero_()
+    return {k: v.clone() for k, v in model.state_dict().items() if "running_" in k and OF.canonical_key(k) == k}
 
+
+def forward_backward(model, loss_mod, args, x, y):
     model.train()
     out = model(x)
     # Model.compute_loss, plt.py:69-77 (plt.py itself cannot be imported here: needs pytorch_lightning/apex)
@@ -85,15 +96,52 @@ def run_case(ref_unet, ref_loss, name, over, batch, size):
         loss = loss_mod(out, y)
         train_logits = out.detach().clone()
     loss.backward()
-    uniq = {}
-    for k, p in model.named_parameters():  # named_parameters de-duplicates shared modules (FusedUNet)
-        uniq[k] = digest(p.grad) if p.grad is not None else None
+    grads = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in model.named_parameters()}
+    return train_logits, float(loss), grads
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+def run_case(ref_unet, ref_loss, name, over, batch, size):
+    import copy
+    args = argparse.Namespace(**{**BASE, **over})
+    model = build_reference_model(ref_unet, args)
+    shapes = {k: (tuple(v.shape), v.dtype) for k, v in model.state_dict().items()}
+    state = OF.deterministic_state(shapes)
+    model.load_state_dict(state, strict=True)
+    x, y = make_inputs(args, batch, size)
+    running = calibrate_running_stats(model, args, x)
+    loss_mod = ref_loss.Loss(args)
+    model64 = copy.deepcopy(model).double()  # the reference modules in fp64: the conditioning yard-stick
+
+    model.eval()
+    model64.eval()
+    with torch.no_grad():
+        eval_logits = model(x).clone()
+        eval_logits64 = model64(x.double()).clone()
+
+    train_logits, loss, grads = forward_backward(model, loss_mod, args, x, y)
+    train_logits64, loss64, grads64 = forward_backward(model64, loss_mod, args, x.double(), y)
+    # named_parameters de-duplicates shared modules (FusedUNet)
+    uniq = {k: (digest(g) if g is not None else None) for k, g in grads.items()}
+    uniq64 = {k: (digest(g) if g is not None else None) for k, g in grads64.items()}
+    noise = {k: (rel(grads[k], grads64[k]) if grads[k] is not None else None) for k in grads}
     post_state = {k: digest(v.float()) for k, v in model.state_dict().items() if "running_" in k}
+    as32 = lambda t: [o.float() for o in t] if isinstance(t, list) else t.float()
+    l32 = train_logits[0] if isinstance(train_logits, list) else train_logits
+    l64 = train_logits64[0] if isinstance(train_logits64, list) else train_logits64
+    print(f"  conditioning (reference fp32 vs fp64): eval logits {rel(eval_logits, eval_logits64):.2e}  train logits "
+          f"{rel(l32, l64):.2e}  grads median {sorted(v for v in noise.values() if v is not None)[len(noise) // 2]:.2e}")
     return {
         "name": name, "args": vars(args), "batch": batch, "size": size, "input_seed": 1, "state_seed": 1,
         "state_shapes": {k: (s, str(d)) for k, (s, d) in shapes.items()},
-        "eval_logits": eval_logits, "train_logits": train_logits, "loss": float(loss),
-        "grad_digest": uniq, "running_digest": post_state,
+        "calibrated_running": running,
+        "eval_logits": eval_logits, "eval_logits64": eval_logits64.float(),
+        "train_logits": train_logits, "train_logits64": as32(train_logits64), "loss": loss, "loss64": loss64,
+        "grad_digest": uniq, "grad_digest64": uniq64, "grad_noise": noise, "running_digest": post_state,
         "torch": torch.__version__,
     }
 

@@ -249,16 +249,27 @@ __global__ void normalize_kernel(const uint8_t* __restrict__ pre, const uint8_t*
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long numel, float lr, float b1, float b2, float eps, float wd,
-                             float bc1, float bc2_sqrt) {
+                             float bc1, float bc2_sqrt, float gscale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel; i += (long long)gridDim.x * blockDim.x) {
     float pi = p[i] * (1.f - lr * wd);
-    const float gi = g[i];
+    const float gi = g[i] * gscale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+// SGD with momentum (dampening 0, no nesterov): buf = mu*buf + g (buf = g on the first step); p -= lr*buf
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long numel,
+                           float lr, float mu, float gscale, int first) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float b = first ? gi : mu * buf[i] + gi;
+    buf[i] = b;
+    p[i] -= lr * b;
   }
 }
 
@@ -399,12 +410,20 @@ extern "C" int xv2_normalize_tiles(const uint8_t* pre, const uint8_t* post, void
 }
 
 extern "C" int xv2_adamw(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1,
-                         float beta2, float eps, float weight_decay, int32_t step, void* stream) {
+                         float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream) {
   XV2_REQUIRE(numel > 0 && step >= 1, "adamw: bad arguments");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   adamw_kernel<<<ew_blocks(numel), 256, 0, as_stream(stream)>>>(p, g, m, v, numel, lr, beta1, beta2, eps, weight_decay,
-                                                                bc1, bc2s);
+                                                                bc1, bc2s, grad_scale);
+  XV2_LAUNCH_CHECK();
+  return XV2_OK;
+}
+
+extern "C" int xv2_sgd(float* p, const float* g, float* buf, int64_t numel, float lr, float momentum, float grad_scale,
+                       int32_t step, void* stream) {
+  XV2_REQUIRE(numel > 0 && step >= 1, "sgd: bad arguments");
+  sgd_kernel<<<ew_blocks(numel), 256, 0, as_stream(stream)>>>(p, g, buf, numel, lr, momentum, grad_scale, step == 1);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }

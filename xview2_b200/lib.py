@@ -71,7 +71,8 @@ _SIGNATURES = {
     "xv2_head_fwd": [P, P, P, P, I64, I32, I32, I32, P],
     "xv2_head_bwd": [P, P, P, P, P, P, I64, I32, I32, I32, P],
     "xv2_normalize_tiles": [P, P, P, I32, I32, I32, I32, P],
-    "xv2_adamw": [P, P, P, P, I64, F, F, F, F, F, I32, P],
+    "xv2_adamw": [P, P, P, P, I64, F, F, F, F, F, I32, F, P],
+    "xv2_sgd": [P, P, P, I64, F, F, F, I32, P],
 }
 
 _lib = None

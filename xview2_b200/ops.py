@@ -40,7 +40,7 @@ def _require_cuda(t):
 # ---------------------------------------------------------------------------------------------------------------
 # packed weights (bf16 / fp32 copies in kernel order), cached per parameter version
 # ---------------------------------------------------------------------------------------------------------------
-_pack_cache = {}
+_pack_epoch = 0  # bumped whenever parameters are rewritten behind autograd's back (optimizer kernels, broadcasts)
 
 
 def _weight_phys(weight):
@@ -51,22 +51,31 @@ def _weight_phys(weight):
 
 
 def pack_weight(weight, mode, dtype, groups=1):
-    """mode 0: [K][R][S][Cg]; mode 1: dgrad order; mode 2: transposed-conv GEMM rows.  Cached until the parameter changes."""
-    w = _weight_phys(weight)
-    key = (weight.data_ptr(), mode, dtype, groups)
-    ver = weight._version
-    hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == ver and hit[1].device == weight.device:
+    """mode 0: [K][R][S][Cg]; mode 1: dgrad order; mode 2: transposed-conv GEMM rows.
+
+    The packed copy lives ON the parameter object (so it dies with it -- a cache keyed by data_ptr would hand a new
+    tensor that reuses the address a stale copy) and is valid for one (tensor version, pack epoch, storage address)."""
+    cache = weight.__dict__.get("_xv2_pack")
+    if cache is None:
+        cache = {}
+        weight.__dict__["_xv2_pack"] = cache
+    stamp = (weight._version, _pack_epoch, weight.data_ptr())
+    hit = cache.get((mode, dtype, groups))
+    if hit is not None and hit[0] == stamp and hit[1].device == weight.device:
         return hit[1]
+    w = _weight_phys(weight)
     a, b, r, s = w.shape
-    out = torch.empty(w.numel(), dtype=dtype, device=w.device)
+    out = hit[1] if hit is not None and hit[1].device == weight.device and hit[1].numel() == w.numel() else \
+        torch.empty(w.numel(), dtype=dtype, device=w.device)
     call("xv2_pack_weight", ptr(w), ptr(out), a, r, s, b, groups, mode, dtype_code(out))
-    _pack_cache[key] = (ver, out)
+    cache[(mode, dtype, groups)] = (stamp, out)
     return out
 
 
 def clear_weight_cache():
-    _pack_cache.clear()
+    """Invalidates every packed weight copy (called after kernels rewrite the master weights in place)."""
+    global _pack_epoch
+    _pack_epoch += 1
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -731,6 +740,10 @@ def normalize_tiles(pre_u8, post_u8=None, dtype=torch.bfloat16):
     return out
 
 
-def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     call("xv2_adamw", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
-         float(weight_decay), int(step))
+         float(weight_decay), int(step), float(grad_scale))
+
+
+def sgd_step(p, g, buf, lr, momentum, grad_scale, step):
+    call("xv2_sgd", ptr(p), ptr(g), ptr(buf), p.numel(), float(lr), float(momentum), float(grad_scale), int(step))
