@@ -226,6 +226,10 @@ int xv2_post_process(const float* loc_logits, const float* dmg_logits, int64_t p
 int xv2_post_process_probs(const float* loc, const float* dmg, int64_t pixels, uint8_t* pre_map, uint8_t* post_map,
                            void* stream);
 
+/* Model.save (plt.py:126-131): probabilities in the layout the reference writes per tile with np.save:
+ * ncls 2: out[n][hw] = sigmoid(logit[..,1]);  ncls 4: out[n][4][hw] = softmax (planar). */
+int xv2_save_probs(const float* logits, int32_t n, int64_t hw, int32_t ncls, float* out, void* stream);
+
 /* 1x1 output head (layers.py:180): logits[p][ncls] (fp32) = x[p][c] . w[ncls][c] + b ; ncls <= 8 */
 int xv2_head_fwd(const void* x, const float* w, const float* b, float* logits, int64_t pixels, int32_t c,
                  int32_t ncls, int32_t dtype, void* stream);

@@ -284,6 +284,27 @@ __global__ void post_process_probs_kernel(const float* __restrict__ loc, const f
   }
 }
 
+// Model.save (plt.py:126-131): logits NHWC [n][hw][ncls] -> probabilities as the reference stores them per tile:
+//   ncls == 2: out[n][hw]      = sigmoid(logit[.., 1])
+//   ncls == 4: out[n][4][hw]   = softmax over the 4 classes (planar, the layout np.save receives)
+template <int NCLS>
+__global__ void save_probs_kernel(const float* __restrict__ logits, long long hw, int n, float* __restrict__ out) {
+  const long long pixels = (long long)n * hw;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < pixels; p += (long long)gridDim.x * blockDim.x) {
+    if (NCLS == 2) {
+      out[p] = 1.f / (1.f + expf(-logits[p * 2 + 1]));
+    } else {
+      const float4 v = *reinterpret_cast<const float4*>(logits + p * 4);
+      const float z[4] = {v.x, v.y, v.z, v.w};
+      float pr[4], lse;
+      softmax_px<4>(z, pr, lse);
+      const long long nb = p / hw, q = p - nb * hw;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) out[(nb * 4 + c) * hw + q] = pr[c];
+    }
+  }
+}
+
 static int loss_blocks(long long pixels) {
   long long b = cdiv(pixels, 256 * 8);
   if (b > 4 * kNumSMs) b = 4 * kNumSMs;
@@ -361,6 +382,16 @@ extern "C" int xv2_post_process_probs(const float* loc, const float* dmg, int64_
                                       uint8_t* post_map, void* stream) {
   XV2_REQUIRE(pixels > 0, "post_process: empty");
   post_process_probs_kernel<<<loss_blocks(pixels), 256, 0, as_stream(stream)>>>(loc, dmg, pixels, pre_map, post_map);
+  XV2_LAUNCH_CHECK();
+  return XV2_OK;
+}
+
+extern "C" int xv2_save_probs(const float* logits, int32_t n, int64_t hw, int32_t ncls, float* out, void* stream) {
+  XV2_REQUIRE(n > 0 && hw > 0, "save_probs: empty");
+  XV2_REQUIRE(ncls == 2 || ncls == 4, "save_probs: ncls %d unsupported (2 or 4)", ncls);
+  const int blocks = loss_blocks((long long)n * hw);
+  if (ncls == 2) save_probs_kernel<2><<<blocks, 256, 0, as_stream(stream)>>>(logits, hw, n, out);
+  else save_probs_kernel<4><<<blocks, 256, 0, as_stream(stream)>>>(logits, hw, n, out);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "xv2_mean4": [P, P, P, P, P, I64, P],
     "xv2_post_process": [P, P, I64, P, P, P],
     "xv2_post_process_probs": [P, P, I64, P, P, P],
+    "xv2_save_probs": [P, I32, I64, I32, P, P],
     "xv2_head_fwd": [P, P, P, P, I64, I32, I32, I32, P],
     "xv2_head_bwd": [P, P, P, P, P, P, I64, I32, I32, I32, P],
     "xv2_normalize_tiles": [P, P, P, I32, I32, I32, I32, P],
@@ -77,6 +78,8 @@ _SIGNATURES = {
 
 _lib = None
 _launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+_profile = None  # when a list: (name, start_event, end_event, flops, bytes) per call -- bench.py's roofline pass
+_work = (0.0, 0.0)  # algorithmic (flops, bytes) of the NEXT call, declared by ops.* through note_work()
 
 
 class Xv2Error(RuntimeError):
@@ -126,11 +129,46 @@ def dtype_code(t):
     raise Xv2Error(f"unsupported activation dtype {t.dtype}")
 
 
+def note_work(flops=0.0, nbytes=0.0):
+    """Declares the algorithmic FLOPs / bytes of the next call (only read while profiling)."""
+    global _work
+    _work = (float(flops), float(nbytes))
+
+
+def profile_start():
+    global _profile
+    _profile = []
+
+
+def profile_stop():
+    """Returns {entry point: {"calls", "ms", "flops", "bytes"}} measured with CUDA events on the launching stream."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, fl, by in rec or []:
+        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += fl
+        d["bytes"] += by
+    return out
+
+
 def call(name, *args, allow_unsupported=False):
     """Calls an entry point with the current stream appended; raises Xv2Error on failure."""
-    global _launches
+    global _launches, _work
     lib = load()
-    rc = getattr(lib, name)(*args, stream_ptr())
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream_ptr())
+        e1.record()
+        if rc == 0:
+            _profile.append((name, e0, e1, _work[0], _work[1]))
+        _work = (0.0, 0.0)
+    else:
+        rc = getattr(lib, name)(*args, stream_ptr())
     if rc == 0:
         _launches += 1
         return 0

@@ -93,6 +93,7 @@ def _conv_gather(src, wpacked, bias, n, h, w, c, oh, ow, k, r, s, stride, pad, d
     out = empty_act(n, k, oh, ow, out_dtype, src.device)
     g = ConvGeom(n, h, w, c, oh, ow, k, r, s, stride, pad, dil, ups, groups, dtype_code(src),
                  F32 if out_dtype == torch.float32 else BF16)
+    lib.note_work(2.0 * n * oh * ow * k * (c // groups) * r * s / (ups * ups), src.element_size() * n * (h * w * c + oh * ow * k))
     call("xv2_conv_gather_simt", g, ptr(src), ptr(wpacked), ptr(bias), ptr(out))
     return out
 
@@ -120,6 +121,7 @@ class _Conv2d(torch.autograd.Function):
             wp = pack_weight(weight, 0, torch.bfloat16, groups)
             out = empty_act(n, k, h, w, x.dtype, x.device)
             p = TcConv(n, h, w, c0, c1, 0, 0, k, r, s, pad, dil, groups, 0, BF16, 0)
+            lib.note_work(2.0 * n * h * w * k * cg * r * s, 2.0 * n * h * w * (c0 + c1 + k) + 2.0 * k * cg * r * s)
             rc = call("xv2_conv_tc", p, ptr(x), ptr(x2), ptr(wp), ptr(bias), ptr(out), None, allow_unsupported=True)
             if rc == 0:
                 return out
@@ -157,6 +159,7 @@ class _Conv2d(torch.autograd.Function):
                         wsub, kk, gg = wt[lo:lo + cc], k, 1
                     o = empty_act(n, cc, h, w, x.dtype, x.device)
                     p = TcConv(n, h, w, kk, 0, 0, 0, cc, r, s, pad_t, dil, gg, 0, BF16, 0)
+                    lib.note_work(2.0 * n * h * w * cc * (k // gg) * r * s, 2.0 * n * h * w * (k + cc) + 2.0 * cc * (k // gg) * r * s)
                     rc = call("xv2_conv_tc", p, ptr(dy), None, ptr(wsub), None, ptr(o), None, allow_unsupported=True)
                     if rc != 0:
                         ok = False
@@ -177,6 +180,7 @@ class _Conv2d(torch.autograd.Function):
             done = False
             if tc:
                 p = TcConv(n, h, w, c0, c1, 0, 0, k, r, s, pad, dil, groups, 0, BF16, 0)
+                lib.note_work(2.0 * n * h * w * k * cg * r * s, 2.0 * n * h * w * (c0 + c1 + k) + 4.0 * k * cg * r * s)
                 rc = call("xv2_wgrad_tc", p, ptr(x), ptr(x2), ptr(dy), 0, ptr(dw), allow_unsupported=True)
                 done = rc == 0
             if not done:
@@ -218,6 +222,7 @@ class _ConvT2x2(torch.autograd.Function):
             wp = pack_weight(weight, 2, torch.bfloat16)
             out = empty_act(n, cout, 2 * h, 2 * w, x.dtype, x.device)
             p = TcConv(n, h, w, cin, 0, 0, 0, cout, 1, 1, 0, 1, 1, 1, BF16, 0)
+            lib.note_work(8.0 * n * h * w * cin * cout, 2.0 * n * h * w * (cin + 4 * cout) + 8.0 * cin * cout)
             rc = call("xv2_conv_tc", p, ptr(x), None, ptr(wp), None, ptr(out), None, allow_unsupported=True)
             if rc == 0:
                 return out
@@ -238,6 +243,7 @@ class _ConvT2x2(torch.autograd.Function):
                 wp = pack_weight(weight, 0, torch.bfloat16)  # physical [cin][kh][kw][cout] is already the GEMM order
                 dx = empty_act(n, cin, h, w, x.dtype, x.device)
                 p = TcConv(n, h, w, cout, 0, 0, 0, cin, 2, 2, 0, 1, 1, 2, BF16, 0)
+                lib.note_work(8.0 * n * h * w * cin * cout, 2.0 * n * h * w * (cin + 4 * cout) + 8.0 * cin * cout)
                 rc = call("xv2_conv_tc", p, ptr(dy), None, ptr(wp), None, ptr(dx), None, allow_unsupported=True)
                 done = rc == 0
             if not done:
@@ -248,6 +254,7 @@ class _ConvT2x2(torch.autograd.Function):
             done = False
             if tc:
                 p = TcConv(n, h, w, cin, 0, 0, 0, cout, 2, 2, 0, 1, 1, 1, BF16, 0)
+                lib.note_work(8.0 * n * h * w * cin * cout, 2.0 * n * h * w * (cin + 4 * cout) + 16.0 * cin * cout)
                 rc = call("xv2_wgrad_tc", p, ptr(x), None, ptr(dy), 0, ptr(dw), allow_unsupported=True)
                 done = rc == 0
             if not done:
@@ -728,6 +735,17 @@ def post_process_probs(loc, dmg):
     post = torch.empty_like(pre)
     call("xv2_post_process_probs", ptr(loc), ptr(dmg), h * w, ptr(pre), ptr(post))
     return pre, post
+
+
+def save_probs(logits):
+    """Model.save (plt.py:126-131): (n, h, w) sigmoid(logit[:, 1]) for the 2-class head, (n, 4, h, w) softmax (plain
+    NCHW, the layout np.save receives) for the 4-class head."""
+    logits = nhwc(logits.detach().float())
+    n, ncls, h, w = logits.shape
+    shape = (n, h, w) if ncls == 2 else (n, ncls, h, w)
+    out = torch.empty(shape, dtype=torch.float32, device=logits.device)
+    call("xv2_save_probs", ptr(logits), n, h * w, ncls, ptr(out))
+    return out
 
 
 def normalize_tiles(pre_u8, post_u8=None, dtype=torch.bfloat16):
