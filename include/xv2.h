@@ -142,11 +142,12 @@ int xv2_bn_bwd_apply(const void* dy, const void* x, const void* residual, void* 
 /* ------------------------------------------------------------------------------------------------------------
  * Pooling, NHWC.  nn.MaxPool2d(3,2,1) unet.py:81; ResNeSt avd AvgPool2d(3,s,1) and avg-down AvgPool2d(s,s,ceil) unet.py:52
  * ---------------------------------------------------------------------------------------------------------- */
-int xv2_maxpool_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh, int32_t ow,
-                    int32_t k, int32_t stride, int32_t pad, int32_t dtype, void* stream);
-/* recomputes the arg-max from x (first maximum in scan order, like ATen) and scatters dy; dx is fully written */
-int xv2_maxpool_bwd(const void* x, const void* dy, void* dx, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh,
+/* idx (optional, uint8 [n][oh][ow][c]): window position r*k+s of the first maximum in scan order (ATen's tie rule) */
+int xv2_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh,
                     int32_t ow, int32_t k, int32_t stride, int32_t pad, int32_t dtype, void* stream);
+/* gathers dy through the saved index map; dx is fully written (no atomics) */
+int xv2_maxpool_bwd(const uint8_t* idx, const void* dy, void* dx, int32_t n, int32_t h, int32_t w, int32_t c,
+                    int32_t oh, int32_t ow, int32_t k, int32_t stride, int32_t pad, int32_t dtype, void* stream);
 int xv2_avgpool_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh, int32_t ow,
                     int32_t k, int32_t stride, int32_t pad, int32_t count_include_pad, int32_t dtype, void* stream);
 int xv2_avgpool_bwd(const void* dy, void* dx, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh, int32_t ow,

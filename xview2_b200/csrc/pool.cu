@@ -29,7 +29,7 @@ struct PoolGeom {
 };
 
 template <typename T, int VEC>
-__global__ void maxpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __restrict__ y) {
+__global__ void maxpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ idx) {
   const int cv = g.c / VEC;
   const long long total = (long long)g.n * g.oh * g.ow * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -40,8 +40,12 @@ __global__ void maxpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __res
     const int oh = (int)(t % g.oh);
     const int nb = (int)(t / g.oh);
     float m[VEC];
+    uint8_t am[VEC];  // window position (r*k + s) of the FIRST maximum in scan order, like ATen
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) m[j] = -INFINITY;
+    for (int j = 0; j < VEC; ++j) {
+      m[j] = -INFINITY;
+      am[j] = 0;
+    }
     for (int r = 0; r < g.k; ++r) {
       const int ih = oh * g.stride - g.pad + r;
       if (ih < 0 || ih >= g.h) continue;
@@ -51,16 +55,27 @@ __global__ void maxpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __res
         float f[VEC];
         pldv<T, VEC>(x + (((long long)nb * g.h + ih) * g.w + iw) * g.c + cvi * VEC, f);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) m[j] = f[j] > m[j] ? f[j] : m[j];
+        for (int j = 0; j < VEC; ++j)
+          if (f[j] > m[j]) {
+            m[j] = f[j];
+            am[j] = (uint8_t)(r * g.k + s);
+          }
       }
     }
-    pstv<T, VEC>(y + (((long long)nb * g.oh + oh) * g.ow + ow) * g.c + cvi * VEC, m);
+    const long long o = (((long long)nb * g.oh + oh) * g.ow + ow) * g.c + cvi * VEC;
+    pstv<T, VEC>(y + o, m);
+    if (idx) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) idx[o + j] = am[j];
+    }
   }
 }
 
-// dx[n,ih,iw,c] = sum over windows (oh,ow) containing (ih,iw) whose FIRST maximum (scan order r,s) is (ih,iw) of dy
+// dx[n,ih,iw,c] = sum over the windows (oh,ow) containing (ih,iw) whose saved arg-max position is (ih,iw) of dy.
+// Gather form: every dx element is written exactly once, no atomics; reads dy + the uint8 index map only.
 template <typename T, int VEC>
-__global__ void maxpool_bwd_kernel(PoolGeom g, const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx) {
+__global__ void maxpool_bwd_kernel(PoolGeom g, const uint8_t* __restrict__ idx, const T* __restrict__ dy,
+                                   T* __restrict__ dx) {
   const int cv = g.c / VEC;
   const long long total = (long long)g.n * g.h * g.w * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -70,11 +85,9 @@ __global__ void maxpool_bwd_kernel(PoolGeom g, const T* __restrict__ x, const T*
     t /= g.w;
     const int ih = (int)(t % g.h);
     const int nb = (int)(t / g.h);
-    float acc[VEC], me[VEC];
+    float acc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-    pldv<T, VEC>(x + (((long long)nb * g.h + ih) * g.w + iw) * g.c + cvi * VEC, me);
-    // windows containing ih: oh*stride - pad <= ih <= oh*stride - pad + k - 1
     int oh_lo = (ih + g.pad - g.k + 1 + g.stride - 1);
     oh_lo = oh_lo < 0 ? 0 : oh_lo / g.stride;
     int oh_hi = (ih + g.pad) / g.stride;
@@ -85,29 +98,23 @@ __global__ void maxpool_bwd_kernel(PoolGeom g, const T* __restrict__ x, const T*
     if (ow_hi > g.ow - 1) ow_hi = g.ow - 1;
     for (int oh = oh_lo; oh <= oh_hi; ++oh) {
       for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-        // position of (ih,iw) in this window's scan order
-        const int my_r = ih - (oh * g.stride - g.pad), my_s = iw - (ow * g.stride - g.pad);
-        bool win[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) win[j] = true;
-        for (int r = 0; r < g.k; ++r) {
-          const int hh = oh * g.stride - g.pad + r;
-          if (hh < 0 || hh >= g.h) continue;
-          for (int s = 0; s < g.k; ++s) {
-            const int ww = ow * g.stride - g.pad + s;
-            if (ww < 0 || ww >= g.w) continue;
-            if (r == my_r && s == my_s) continue;
-            float f[VEC];
-            pldv<T, VEC>(x + (((long long)nb * g.h + hh) * g.w + ww) * g.c + cvi * VEC, f);
-            const bool before = (r < my_r) || (r == my_r && s < my_s);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) win[j] = win[j] && (before ? (f[j] < me[j]) : (f[j] <= me[j]));
-          }
-        }
+        const int mine = (ih - (oh * g.stride - g.pad)) * g.k + (iw - (ow * g.stride - g.pad));
+        const long long o = (((long long)nb * g.oh + oh) * g.ow + ow) * g.c + cvi * VEC;
         float d[VEC];
-        pldv<T, VEC>(dy + (((long long)nb * g.oh + oh) * g.ow + ow) * g.c + cvi * VEC, d);
+        pldv<T, VEC>(dy + o, d);
+        if constexpr (VEC == 8) {
+          const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
+          const uint32_t w2[2] = {pk.x, pk.y};
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] += win[j] ? d[j] : 0.f;
+          for (int j = 0; j < 8; ++j) acc[j] += (int)((w2[j >> 2] >> (8 * (j & 3))) & 0xFF) == mine ? d[j] : 0.f;
+        } else if constexpr (VEC == 4) {
+          const uint32_t pk = *reinterpret_cast<const uint32_t*>(idx + o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] += (int)((pk >> (8 * j)) & 0xFF) == mine ? d[j] : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[j] += (int)idx[o + j] == mine ? d[j] : 0.f;
+        }
       }
     }
     pstv<T, VEC>(dx + (((long long)nb * g.h + ih) * g.w + iw) * g.c + cvi * VEC, acc);
@@ -215,19 +222,21 @@ using namespace xv2;
     XV2_LAUNCH_CHECK();                                                                         \
   } while (0)
 
-extern "C" int xv2_maxpool_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh,
-                               int32_t ow, int32_t k, int32_t stride, int32_t pad, int32_t dtype, void* stream) {
-  XV2_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0 && k > 0 && stride > 0, "maxpool: bad shape");
-  PoolGeom g{n, h, w, c, oh, ow, k, stride, pad, 0};
-  XV2_POOL_LAUNCH(maxpool_fwd_kernel, (long long)n * oh * ow, g, (const T*)x, (T*)y);
-  return XV2_OK;
-}
-extern "C" int xv2_maxpool_bwd(const void* x, const void* dy, void* dx, int32_t n, int32_t h, int32_t w, int32_t c,
+extern "C" int xv2_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t n, int32_t h, int32_t w, int32_t c,
                                int32_t oh, int32_t ow, int32_t k, int32_t stride, int32_t pad, int32_t dtype,
                                void* stream) {
-  XV2_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0 && k > 0 && stride > 0, "maxpool: bad shape");
+  XV2_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0 && k > 0 && k <= 15 && stride > 0, "maxpool: bad shape");
   PoolGeom g{n, h, w, c, oh, ow, k, stride, pad, 0};
-  XV2_POOL_LAUNCH(maxpool_bwd_kernel, (long long)n * h * w, g, (const T*)x, (const T*)dy, (T*)dx);
+  XV2_POOL_LAUNCH(maxpool_fwd_kernel, (long long)n * oh * ow, g, (const T*)x, (T*)y, idx);
+  return XV2_OK;
+}
+extern "C" int xv2_maxpool_bwd(const uint8_t* idx, const void* dy, void* dx, int32_t n, int32_t h, int32_t w,
+                               int32_t c, int32_t oh, int32_t ow, int32_t k, int32_t stride, int32_t pad,
+                               int32_t dtype, void* stream) {
+  XV2_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0 && k > 0 && stride > 0, "maxpool: bad shape");
+  XV2_REQUIRE(idx != nullptr, "maxpool_bwd: index map missing");
+  PoolGeom g{n, h, w, c, oh, ow, k, stride, pad, 0};
+  XV2_POOL_LAUNCH(maxpool_bwd_kernel, (long long)n * h * w, g, idx, (const T*)dy, (T*)dx);
   return XV2_OK;
 }
 extern "C" int xv2_avgpool_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh,

@@ -45,7 +45,7 @@ _SIGNATURES = {
     "xv2_bn_apply": [P, P, P, I64, I32, I32, P, P, I32, P],
     "xv2_bn_bwd_reduce": [P, P, P, I64, I32, I32, P, P, P, P, I32, P, P],
     "xv2_bn_bwd_apply": [P, P, P, P, P, I64, I32, I32, P, P, P, P, P, I32, P, I64, P, P, P],
-    "xv2_maxpool_fwd": [P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
+    "xv2_maxpool_fwd": [P, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
     "xv2_maxpool_bwd": [P, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
     "xv2_avgpool_fwd": [P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
     "xv2_avgpool_bwd": [P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
@@ -79,7 +79,7 @@ _SIGNATURES = {
 _lib = None
 _launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
 _profile = None  # when a list: (name, start_event, end_event, flops, bytes) per call -- bench.py's roofline pass
-_work = (0.0, 0.0)  # algorithmic (flops, bytes) of the NEXT call, declared by ops.* through note_work()
+_work = (0.0, 0.0, "")  # algorithmic (flops, bytes, tag) of the NEXT call, declared by ops.* through note_work()
 
 
 class Xv2Error(RuntimeError):
@@ -129,10 +129,10 @@ def dtype_code(t):
     raise Xv2Error(f"unsupported activation dtype {t.dtype}")
 
 
-def note_work(flops=0.0, nbytes=0.0):
-    """Declares the algorithmic FLOPs / bytes of the next call (only read while profiling)."""
+def note_work(flops=0.0, nbytes=0.0, tag=""):
+    """Declares the algorithmic FLOPs / bytes (and a shape tag) of the next call (only read while profiling)."""
     global _work
-    _work = (float(flops), float(nbytes))
+    _work = (float(flops), float(nbytes), tag)
 
 
 def profile_start():
@@ -140,13 +140,16 @@ def profile_start():
     _profile = []
 
 
-def profile_stop():
-    """Returns {entry point: {"calls", "ms", "flops", "bytes"}} measured with CUDA events on the launching stream."""
+def profile_stop(per_call=False):
+    """Returns {entry point: {"calls", "ms", "flops", "bytes"}} measured with CUDA events on the launching stream
+    (per_call=True: the raw list of (entry point, tag, ms, flops, bytes) instead)."""
     global _profile
     rec, _profile = _profile, None
     torch.cuda.synchronize()
+    if per_call:
+        return [(name, tag, e0.elapsed_time(e1), fl, by) for name, e0, e1, fl, by, tag in rec or []]
     out = {}
-    for name, e0, e1, fl, by in rec or []:
+    for name, e0, e1, fl, by, _tag in rec or []:
         d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
         d["calls"] += 1
         d["ms"] += e0.elapsed_time(e1)
@@ -165,8 +168,8 @@ def call(name, *args, allow_unsupported=False):
         rc = getattr(lib, name)(*args, stream_ptr())
         e1.record()
         if rc == 0:
-            _profile.append((name, e0, e1, _work[0], _work[1]))
-        _work = (0.0, 0.0)
+            _profile.append((name, e0, e1, _work[0], _work[1], _work[2]))
+        _work = (0.0, 0.0, "")
     else:
         rc = getattr(lib, name)(*args, stream_ptr())
     if rc == 0:

@@ -93,7 +93,8 @@ def _conv_gather(src, wpacked, bias, n, h, w, c, oh, ow, k, r, s, stride, pad, d
     out = empty_act(n, k, oh, ow, out_dtype, src.device)
     g = ConvGeom(n, h, w, c, oh, ow, k, r, s, stride, pad, dil, ups, groups, dtype_code(src),
                  F32 if out_dtype == torch.float32 else BF16)
-    lib.note_work(2.0 * n * oh * ow * k * (c // groups) * r * s / (ups * ups), src.element_size() * n * (h * w * c + oh * ow * k))
+    lib.note_work(2.0 * n * oh * ow * k * (c // groups) * r * s / (ups * ups), src.element_size() * n * (h * w * c + oh * ow * k),
+                  f"simt n{n} {h}x{w}->{oh}x{ow} c{c} k{k} {r}x{s} s{stride} g{groups} u{ups}")
     call("xv2_conv_gather_simt", g, ptr(src), ptr(wpacked), ptr(bias), ptr(out))
     return out
 
@@ -121,7 +122,8 @@ class _Conv2d(torch.autograd.Function):
             wp = pack_weight(weight, 0, torch.bfloat16, groups)
             out = empty_act(n, k, h, w, x.dtype, x.device)
             p = TcConv(n, h, w, c0, c1, 0, 0, k, r, s, pad, dil, groups, 0, BF16, 0)
-            lib.note_work(2.0 * n * h * w * k * cg * r * s, 2.0 * n * h * w * (c0 + c1 + k) + 2.0 * k * cg * r * s)
+            lib.note_work(2.0 * n * h * w * k * cg * r * s, 2.0 * n * h * w * (c0 + c1 + k) + 2.0 * k * cg * r * s,
+                          f"fwd n{n} {h}x{w} c{c0}+{c1} k{k} {r}x{s} g{groups}")
             rc = call("xv2_conv_tc", p, ptr(x), ptr(x2), ptr(wp), ptr(bias), ptr(out), None, allow_unsupported=True)
             if rc == 0:
                 return out
@@ -159,7 +161,8 @@ class _Conv2d(torch.autograd.Function):
                         wsub, kk, gg = wt[lo:lo + cc], k, 1
                     o = empty_act(n, cc, h, w, x.dtype, x.device)
                     p = TcConv(n, h, w, kk, 0, 0, 0, cc, r, s, pad_t, dil, gg, 0, BF16, 0)
-                    lib.note_work(2.0 * n * h * w * cc * (k // gg) * r * s, 2.0 * n * h * w * (k + cc) + 2.0 * cc * (k // gg) * r * s)
+                    lib.note_work(2.0 * n * h * w * cc * (k // gg) * r * s, 2.0 * n * h * w * (k + cc) + 2.0 * cc * (k // gg) * r * s,
+                                  f"dgrad n{n} {h}x{w} c{k} k{cc} {r}x{s} g{gg}")
                     rc = call("xv2_conv_tc", p, ptr(dy), None, ptr(wsub), None, ptr(o), None, allow_unsupported=True)
                     if rc != 0:
                         ok = False
@@ -180,7 +183,8 @@ class _Conv2d(torch.autograd.Function):
             done = False
             if tc:
                 p = TcConv(n, h, w, c0, c1, 0, 0, k, r, s, pad, dil, groups, 0, BF16, 0)
-                lib.note_work(2.0 * n * h * w * k * cg * r * s, 2.0 * n * h * w * (c0 + c1 + k) + 4.0 * k * cg * r * s)
+                lib.note_work(2.0 * n * h * w * k * cg * r * s, 2.0 * n * h * w * (c0 + c1 + k) + 4.0 * k * cg * r * s,
+                              f"wgrad n{n} {h}x{w} c{c0}+{c1} k{k} {r}x{s} g{groups}")
                 rc = call("xv2_wgrad_tc", p, ptr(x), ptr(x2), ptr(dy), 0, ptr(dw), allow_unsupported=True)
                 done = rc == 0
             if not done:
@@ -222,7 +226,8 @@ class _ConvT2x2(torch.autograd.Function):
             wp = pack_weight(weight, 2, torch.bfloat16)
             out = empty_act(n, cout, 2 * h, 2 * w, x.dtype, x.device)
             p = TcConv(n, h, w, cin, 0, 0, 0, cout, 1, 1, 0, 1, 1, 1, BF16, 0)
-            lib.note_work(8.0 * n * h * w * cin * cout, 2.0 * n * h * w * (cin + 4 * cout) + 8.0 * cin * cout)
+            lib.note_work(8.0 * n * h * w * cin * cout, 2.0 * n * h * w * (cin + 4 * cout) + 8.0 * cin * cout,
+                          f"convT fwd n{n} {h}x{w} c{cin} k{cout}")
             rc = call("xv2_conv_tc", p, ptr(x), None, ptr(wp), None, ptr(out), None, allow_unsupported=True)
             if rc == 0:
                 return out
@@ -243,7 +248,8 @@ class _ConvT2x2(torch.autograd.Function):
                 wp = pack_weight(weight, 0, torch.bfloat16)  # physical [cin][kh][kw][cout] is already the GEMM order
                 dx = empty_act(n, cin, h, w, x.dtype, x.device)
                 p = TcConv(n, h, w, cout, 0, 0, 0, cin, 2, 2, 0, 1, 1, 2, BF16, 0)
-                lib.note_work(8.0 * n * h * w * cin * cout, 2.0 * n * h * w * (cin + 4 * cout) + 8.0 * cin * cout)
+                lib.note_work(8.0 * n * h * w * cin * cout, 2.0 * n * h * w * (cin + 4 * cout) + 8.0 * cin * cout,
+                              f"convT dgrad n{n} {h}x{w} c{cout} k{cin}")
                 rc = call("xv2_conv_tc", p, ptr(dy), None, ptr(wp), None, ptr(dx), None, allow_unsupported=True)
                 done = rc == 0
             if not done:
@@ -254,7 +260,8 @@ class _ConvT2x2(torch.autograd.Function):
             done = False
             if tc:
                 p = TcConv(n, h, w, cin, 0, 0, 0, cout, 2, 2, 0, 1, 1, 1, BF16, 0)
-                lib.note_work(8.0 * n * h * w * cin * cout, 2.0 * n * h * w * (cin + 4 * cout) + 16.0 * cin * cout)
+                lib.note_work(8.0 * n * h * w * cin * cout, 2.0 * n * h * w * (cin + 4 * cout) + 16.0 * cin * cout,
+                              f"convT wgrad n{n} {h}x{w} c{cin} k{cout}")
                 rc = call("xv2_wgrad_tc", p, ptr(x), None, ptr(dy), 0, ptr(dw), allow_unsupported=True)
                 done = rc == 0
             if not done:
@@ -356,19 +363,19 @@ class _MaxPool(torch.autograd.Function):
         n, c, h, w = x.shape
         oh, ow = _pool_out(h, k, stride, pad, False), _pool_out(w, k, stride, pad, False)
         y = empty_act(n, c, oh, ow, x.dtype, x.device)
-        call("xv2_maxpool_fwd", ptr(x), ptr(y), n, h, w, c, oh, ow, k, stride, pad, dtype_code(x))
-        ctx.save_for_backward(x)
-        ctx.cfg = (k, stride, pad, oh, ow)
+        idx = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device) if ctx.needs_input_grad[0] else None
+        call("xv2_maxpool_fwd", ptr(x), ptr(y), ptr(idx), n, h, w, c, oh, ow, k, stride, pad, dtype_code(x))
+        ctx.save_for_backward(idx)
+        ctx.cfg = (k, stride, pad, oh, ow, n, c, h, w)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
-        k, stride, pad, oh, ow = ctx.cfg
+        (idx,) = ctx.saved_tensors
+        k, stride, pad, oh, ow, n, c, h, w = ctx.cfg
         dy = nhwc(dy)
-        n, c, h, w = x.shape
-        dx = torch.empty_like(x)
-        call("xv2_maxpool_bwd", ptr(x), ptr(dy), ptr(dx), n, h, w, c, oh, ow, k, stride, pad, dtype_code(x))
+        dx = empty_act(n, c, h, w, dy.dtype, dy.device)
+        call("xv2_maxpool_bwd", ptr(idx), ptr(dy), ptr(dx), n, h, w, c, oh, ow, k, stride, pad, dtype_code(dy))
         return dx, None, None, None
 
 
