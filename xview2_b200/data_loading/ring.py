@@ -11,6 +11,7 @@ Normalize + HWC->NHWC-bf16 conversion is one kernel on the device (xv2_normalize
     batch = ring.acquire(i)        # compute stream waits for the copy; device tensors
     ...                            # training_step(batch)
     ring.release(i)                # slot may be overwritten once the compute stream got here
+    ring.wait_free(i)              # host: the copy out of host slot i is done, decode threads may refill it
 """
 import torch
 
@@ -29,14 +30,23 @@ class TileRing:
         self._free = [torch.cuda.Event() for _ in range(slots)]
         for e in self._free:
             e.record(torch.cuda.current_stream(self.device))
+        self._submitted = [False] * slots
+        self.batch, self.hw = batch, (h, w)
         self.bytes_per_batch = sum(t.numel() for t in self._host[0].values())
 
     def host(self, i):
         """Pinned host tensors of slot i (fill them in place; `.numpy()` views share the memory)."""
         return self._host[i % self.slots]
 
+    def wait_free(self, i):
+        """Host-side: blocks until the last H2D copy out of host slot i has finished, so the slot may be refilled."""
+        s = i % self.slots
+        if self._submitted[s]:
+            self._ready[s].synchronize()
+
     def submit(self, i):
         s = i % self.slots
+        self._submitted[s] = True
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self._free[s])
             for k, t in self._host[s].items():
