@@ -22,6 +22,13 @@ CASES = {
     "cat_32_32_k32_3x3": ("conv", 2, 32, 32, 16, 32, 32, 3, 1, 1),
     "dil2_c64_k64": ("conv", 1, 64, 0, 16, 16, 64, 3, 2, 1),
     "c256_k96_3x3_w256": ("conv", 1, 256, 0, 2, 256, 96, 3, 1, 1),     # N tile not a power of two
+    # row-strip kernel shapes (w % 128 == 0, <= 128 channels per group): ring wrap, pieces crossing columns / images
+    "strip_c32_k32_w256": ("conv", 3, 32, 0, 100, 256, 32, 3, 1, 1),
+    "strip_c64_k64_w128": ("conv", 2, 64, 0, 37, 128, 64, 3, 1, 1),
+    "strip_c32_k64_w128": ("conv", 2, 32, 0, 64, 128, 64, 3, 1, 1),
+    "strip_cat_64_64_k64_w128": ("conv", 2, 64, 64, 48, 128, 64, 3, 1, 1),
+    "strip_g2_c64_k128_w128": ("conv", 2, 64, 0, 40, 128, 128, 3, 1, 2),
+    "strip_g2_c128_k256_w128": ("conv", 1, 128, 0, 33, 128, 256, 3, 1, 2),
     "convt_c128_k64": ("convt", 2, 128, 0, 16, 16, 64, 2, 1, 1),
     "convt_c64_k32_w64": ("convt", 1, 64, 0, 8, 64, 32, 2, 1, 1),
     "convt_c2048_k512": ("convt", 1, 2048, 0, 16, 8, 512, 2, 1, 1),

@@ -1,0 +1,349 @@
+// Row-strip 3x3 convolution for the HBM-bound layers (few channels, large images): forward / data gradient.
+//
+// Why a second kernel: at 32-128 channels a 3x3 convolution moves ~2 bytes per 300-600 FLOPs, i.e. it is bound by HBM,
+// but the tile-per-tap kernel (conv_tc.cu) re-fetches the activation tile once per tap (9x through L2) and the weights
+// once per tile.  Here a CTA walks DOWN a 128-pixel-wide column of one image:
+//   * every input row (128 + 2 halo pixels, all channels of the group) is fetched ONCE by TMA into a ring of row slots in
+//     shared memory (out-of-image halo pixels / rows are zero-filled by the TMA unit = the "same" padding);
+//   * the 9 taps are 9 UMMA descriptors into that ring: tap row r picks the slot, tap column s SHIFTS THE DESCRIPTOR START
+//     by s pixel rows (the 128B / 64B swizzle is a function of the absolute shared-memory address, so a shifted start
+//     reads exactly what TMA wrote; measured on B200: profiles/r01_umma_shift_probe.txt);
+//   * the weights of the (group, n-tile) stay resident in shared memory for the whole column;
+//   * accumulators live in TMEM (double buffered); 4-8 epilogue warps convert to bf16, store, and reduce the per-channel
+//     sum / sum of squares of the ROUNDED outputs (nn.BatchNorm2d statistics, layers.py:93) with a 31-step shuffle
+//     transpose so that the statistics pass over the output disappears.
+// HBM traffic = input once + output once; L2->SM traffic = the same (+2 halo rows per piece).
+//
+// Work split: the (weight set, image, column, row) space is linearised and cut into gridDim.x equal contiguous pieces.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace xv2 {
+using namespace tc;
+
+int strip_encode_act(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int ld, int box_c, int box_w);
+int strip_encode_weight(CUtensorMap* m, const void* ptr, long long rows, long long kdim, int box_k, int box_rows);
+int tc_num_sms();
+
+constexpr int kStripPix = 128;               // output pixels per row tile (UMMA M)
+constexpr int kStripHalo = kStripPix + 2;    // input pixels fetched per row
+constexpr int kStripPitch = 136;             // row pitch of a slot in pixels (multiple of 8: slots stay swizzle-aligned)
+constexpr int kStripMaxRing = 12;
+
+struct alignas(64) StripParams {
+  CUtensorMap map_a0, map_a1, map_b;
+  int n, h, w, wtiles;
+  int groups, n_tiles;      // weight sets = groups * n_tiles
+  int cg, kg, bn;           // in / out channels per group, N tile
+  int chunks, chunks0;      // channel chunks (of BK) per input row: total / taken from source 0
+  int ring;                 // row slots
+  int k_total, ldo;
+  long long rows_total;     // wsets * n * wtiles * h
+  __nv_bfloat16* out;
+  double* stats;            // optional [2 * k_total]
+};
+
+struct Piece {
+  int wset, img, wt, ha, hb;
+};
+// piece of the linear row space [lo, hi) that starts at lo and ends at the column boundary or hi
+__device__ __forceinline__ Piece piece_at(long long lo, long long hi, int h, int wtiles, int n) {
+  Piece p;
+  long long col = lo / h;
+  p.ha = (int)(lo - col * h);
+  long long len = hi - lo;
+  p.hb = (int)((long long)p.ha + len < (long long)h ? p.ha + len : h);
+  p.wt = (int)(col % wtiles);
+  col /= wtiles;
+  p.img = (int)(col % n);
+  p.wset = (int)(col / n);
+  return p;
+}
+
+template <int BK>
+__global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constant__ StripParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t ROWB = BK * 2;                    // bytes per pixel row of a chunk = swizzle span
+  constexpr uint32_t CHUNK_BYTES = kStripPitch * ROWB;  // multiple of the swizzle pattern (8 rows)
+  const uint32_t tile_bytes = (uint32_t)p.bn * ROWB;   // one (tap, chunk) weight tile
+  const uint32_t w_bytes = 9u * p.chunks * tile_bytes;
+  const uint32_t slot_bytes = (uint32_t)p.chunks * CHUNK_BYTES;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring0 = base + ((w_bytes + 1023u) & ~1023u);
+  const uint32_t bar_base = ring0 + p.ring * slot_bytes;
+  const uint32_t full0 = bar_base, empty0 = bar_base + 8 * kStripMaxRing, wfull = empty0 + 8 * kStripMaxRing;
+  const uint32_t tfull0 = wfull + 8, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int epi_warps = p.bn >= 64 ? 8 : 4;
+  const uint32_t tmem_cols = p.bn <= 16 ? 32u : (p.bn <= 32 ? 64u : (p.bn <= 64 ? 128u : 256u));  // 2 accumulators
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.map_a0);
+    tma_prefetch_desc(&p.map_b);
+    if (p.chunks > p.chunks0) tma_prefetch_desc(&p.map_a1);
+    for (int s = 0; s < p.ring; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(wfull, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, epi_warps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const long long lo0 = p.rows_total * blockIdx.x / gridDim.x;
+  const long long hi0 = p.rows_total * (blockIdx.x + 1) / gridDim.x;
+  const uint32_t R = (uint32_t)p.ring;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    uint32_t g = 0;
+    int cur_wset = -1;
+    for (long long lo = lo0; lo < hi0;) {
+      const Piece pc = piece_at(lo, hi0, p.h, p.wtiles, p.n);
+      lo += pc.hb - pc.ha;
+      const int grp = pc.wset / p.n_tiles, nt = pc.wset - grp * p.n_tiles;
+      if (pc.wset != cur_wset) {
+        // every MMA that reads the resident weights has completed once all row slots have been released
+        for (uint32_t j = 0; j < R; ++j) mbar_wait(empty0 + 8 * ((g + j) % R), (((g + j) / R) & 1) ^ 1);
+        mbar_expect_tx(wfull, w_bytes);
+        for (int t = 0; t < 9; ++t)
+          for (int ch = 0; ch < p.chunks; ++ch)
+            tma_load_2d(base + (uint32_t)(t * p.chunks + ch) * tile_bytes, &p.map_b, wfull, t * p.cg + ch * BK,
+                        grp * p.kg + nt * p.bn);
+        cur_wset = pc.wset;
+      }
+      for (int row = pc.ha - 1; row <= pc.hb; ++row, ++g) {
+        const uint32_t slot = g % R;
+        mbar_wait(empty0 + 8 * slot, ((g / R) & 1) ^ 1);
+        const uint32_t fb = full0 + 8 * slot;
+        mbar_expect_tx(fb, (uint32_t)p.chunks * kStripHalo * ROWB);
+        const uint32_t dst = ring0 + slot * slot_bytes;
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          if (ch < p.chunks0)
+            tma_load_4d(dst + ch * CHUNK_BYTES, &p.map_a0, fb, grp * p.cg + ch * BK, pc.wt * kStripPix - 1, row, pc.img);
+          else
+            tma_load_4d(dst + ch * CHUNK_BYTES, &p.map_a1, fb, (ch - p.chunks0) * BK, pc.wt * kStripPix - 1, row, pc.img);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.bn, 0, 0);
+    uint32_t g = 0, acc = 0, acc_phase = 0, wphase = 0;
+    int cur_wset = -1;
+    for (long long lo = lo0; lo < hi0;) {
+      const Piece pc = piece_at(lo, hi0, p.h, p.wtiles, p.n);
+      const int nrows = pc.hb - pc.ha;
+      lo += nrows;
+      if (pc.wset != cur_wset) {
+        mbar_wait(wfull, wphase);
+        wphase ^= 1;
+        cur_wset = pc.wset;
+      }
+      mbar_wait(full0 + 8 * (g % R), (g / R) & 1);
+      mbar_wait(full0 + 8 * ((g + 1) % R), ((g + 1) / R) & 1);
+      for (int i = 0; i < nrows; ++i) {
+        mbar_wait(full0 + 8 * ((g + i + 2) % R), ((g + i + 2) / R) & 1);
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * (tmem_cols >> 1);
+        uint32_t accum = 0;
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+          const uint32_t row_base = ring0 + ((g + i + r) % R) * slot_bytes;
+#pragma unroll 1
+          for (int s = 0; s < 3; ++s) {
+            for (int ch = 0; ch < p.chunks; ++ch) {
+              const uint64_t ad = make_smem_desc(row_base + ch * CHUNK_BYTES + s * ROWB, 16, 8 * ROWB, ROWB);
+              const uint64_t bd = make_smem_desc(base + (uint32_t)((r * 3 + s) * p.chunks + ch) * tile_bytes, 16, 8 * ROWB, ROWB);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, accum);
+                accum = 1;
+              }
+            }
+          }
+        }
+        umma_commit(tfull0 + 8 * acc);
+        umma_commit(empty0 + 8 * ((g + i) % R));  // input row ha-1+i is not needed by later output rows
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      umma_commit(empty0 + 8 * ((g + nrows) % R));
+      umma_commit(empty0 + 8 * ((g + nrows + 1) % R));
+      g += nrows + 2;
+    }
+  } else if (warp >= 2 && warp < 2 + epi_warps) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int cgrp = (warp - 2) >> 2;          // column group (0 | 1)
+    const int cgroups = epi_warps >> 2;
+    const int m = q * 32 + lane;               // pixel within the row tile
+    uint32_t acc = 0, acc_phase = 0;
+    for (long long lo = lo0; lo < hi0;) {
+      const Piece pc = piece_at(lo, hi0, p.h, p.wtiles, p.n);
+      const int nrows = pc.hb - pc.ha;
+      lo += nrows;
+      const int grp = pc.wset / p.n_tiles, nt = pc.wset - grp * p.n_tiles;
+      const int co0 = grp * p.kg + nt * p.bn;
+      float ssum0 = 0.f, ssq0 = 0.f, ssum1 = 0.f, ssq1 = 0.f;  // lane j: channel (block*32 + j) after the transpose-reduce
+      for (int i = 0; i < nrows; ++i) {
+        const long long pix = ((long long)pc.img * p.h + (pc.ha + i)) * p.w + pc.wt * kStripPix + m;
+        mbar_wait(tfull0 + 8 * acc, acc_phase);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (tmem_cols >> 1);
+        int bi = 0;
+        for (int c0 = cgrp * 32; c0 < p.bn; c0 += cgroups * 32, ++bi) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + c0, v);
+          tmem_ld_wait();
+          float f[32];
+          __nv_bfloat16* o = p.out + pix * p.ldo + co0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              __nv_bfloat162 hp = __floats2bfloat162_rn(__uint_as_float(v[j + 2 * t]), __uint_as_float(v[j + 2 * t + 1]));
+              w4[t] = *reinterpret_cast<uint32_t*>(&hp);
+              f[j + 2 * t] = __uint_as_float(w4[t] << 16);
+              f[j + 2 * t + 1] = __uint_as_float(w4[t] & 0xffff0000u);
+            }
+            *reinterpret_cast<uint4*>(o + j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+          if (p.stats) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+            // transpose-reduce: after the 5 steps lane j holds the sum over the warp's 32 pixels of column j
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+              const bool up = (lane & s) != 0;
+#pragma unroll
+              for (int j = 0; j < s; ++j) {
+                const float keep = up ? f[j + s] : f[j], send = up ? f[j] : f[j + s];
+                f[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                const float keep2 = up ? sq[j + s] : sq[j], send2 = up ? sq[j] : sq[j + s];
+                sq[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, s);
+              }
+            }
+            if (bi == 0) {
+              ssum0 += f[0];
+              ssq0 += sq[0];
+            } else {
+              ssum1 += f[0];
+              ssq1 += sq[0];
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (p.stats) {
+        int bi = 0;
+        for (int c0 = cgrp * 32; c0 < p.bn; c0 += cgroups * 32, ++bi) {
+          atomicAdd(p.stats + co0 + c0 + lane, (double)(bi == 0 ? ssum0 : ssum1));
+          atomicAdd(p.stats + p.k_total + co0 + c0 + lane, (double)(bi == 0 ? ssq0 : ssq1));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// Host side.  Returns XV2_EUNSUPPORTED when the shape is not a strip shape (caller uses the tile-per-tap kernel).
+int conv_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, const void* w, void* out, double* stats,
+                      void* stream) {
+  const int groups = q->groups < 1 ? 1 : q->groups;
+  const int ld0 = q->ld0 ? q->ld0 : q->c0, ld1 = q->ld1 ? q->ld1 : q->c1;
+  const int ctot = q->c0 + q->c1;
+  if (q->convt || q->r != 3 || q->s != 3 || q->pad != 1 || (q->dil > 1) || q->out_dtype != XV2_BF16 || q->w % kStripPix ||
+      ctot % groups || q->k % groups || (groups > 1 && q->c1) || ld0 % 8 || (q->c1 && ld1 % 8))
+    return XV2_EUNSUPPORTED;
+  const int cg = ctot / groups, kg = q->k / groups;
+  if (!(cg == 32 || cg == 64 || cg == 128) || kg % 32) return XV2_EUNSUPPORTED;
+  if (q->c1 && (q->c0 % 64 || q->c1 % 64)) return XV2_EUNSUPPORTED;
+  if (cg == 128 && kg > 64) return XV2_EUNSUPPORTED;  // compute-bound: the tile-per-tap kernel with a wide N is the better fit
+  const int bk = cg == 32 ? 32 : 64;
+  const int chunks = cg / bk;
+  const uint32_t rowb = bk * 2, chunk_bytes = kStripPitch * rowb, slot_bytes = chunks * chunk_bytes;
+  const uint32_t budget = 232448 - 1024 - 512;
+  int bn = 0, ring = 0;
+  for (int cand : {128, 64, 32}) {
+    if (kg % cand) continue;
+    if (cg == 128 && cand > 32) continue;
+    const uint32_t wb = ((9u * chunks * cand * rowb) + 1023u) & ~1023u;
+    if (wb + 4 * slot_bytes > budget) continue;
+    bn = cand;
+    ring = (int)((budget - wb) / slot_bytes);
+    break;
+  }
+  if (!bn) return XV2_EUNSUPPORTED;
+  if (ring > kStripMaxRing) ring = kStripMaxRing;
+  const int ldo = q->ldo ? q->ldo : q->k;
+  if (ldo % 8) return XV2_EUNSUPPORTED;
+
+  StripParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = strip_encode_act(&p.map_a0, src0, q->n, q->h, q->w, q->c0, ld0, bk, kStripHalo);
+  if (!rc && q->c1) rc = strip_encode_act(&p.map_a1, src1, q->n, q->h, q->w, q->c1, ld1, bk, kStripHalo);
+  if (!rc) rc = strip_encode_weight(&p.map_b, w, q->k, 9LL * cg, bk, bn);
+  if (rc) return rc;
+  p.n = q->n;
+  p.h = q->h;
+  p.w = q->w;
+  p.wtiles = q->w / kStripPix;
+  p.groups = groups;
+  p.n_tiles = kg / bn;
+  p.cg = cg;
+  p.kg = kg;
+  p.bn = bn;
+  p.chunks = chunks;
+  p.chunks0 = groups > 1 ? chunks : q->c0 / bk;
+  p.ring = ring;
+  p.k_total = q->k;
+  p.ldo = ldo;
+  p.rows_total = (long long)groups * p.n_tiles * q->n * p.wtiles * q->h;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.stats = stats;
+  const uint32_t wb = ((9u * chunks * bn * rowb) + 1023u) & ~1023u;
+  const size_t smem = 1024 + wb + (size_t)ring * slot_bytes + 512;
+  long long grid = tc_num_sms();
+  if (grid > p.rows_total / 16) grid = p.rows_total / 16 > 0 ? p.rows_total / 16 : 1;
+  cudaError_t e;
+  if (bk == 64) {
+    e = cudaFuncSetAttribute(conv_strip_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv_strip_kernel<64><<<(unsigned)grid, 320, smem, as_stream(stream)>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(conv_strip_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv_strip_kernel<32><<<(unsigned)grid, 320, smem, as_stream(stream)>>>(p);
+  }
+  if (e != cudaSuccess) {
+    set_error("conv_strip: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    return XV2_ECUDA;
+  }
+  XV2_LAUNCH_CHECK();
+  return XV2_OK;
+}
+
+}  // namespace xv2

@@ -21,6 +21,8 @@
 //   * split over pixel tiles; fp32 partial tiles are reduced into dW with red.global.add.f32.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace xv2 {
 using namespace tc;
@@ -483,6 +485,25 @@ static int encode_weight_map(CUtensorMap* m, const void* ptr, long long rows, lo
   return XV2_OK;
 }
 
+// shared with conv_strip.cu / wgrad_strip.cu
+int strip_encode_act(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int ld, int box_c, int box_w) {
+  return encode_act_map(m, ptr, n, h, w, c, ld, box_c, box_w, 1);
+}
+int strip_encode_weight(CUtensorMap* m, const void* ptr, long long rows, long long kdim, int box_k, int box_rows) {
+  return encode_weight_map(m, ptr, rows, kdim, box_k, box_rows);
+}
+int tc_num_sms() { return g_num_sms; }
+int conv_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, const void* w, void* out, double* stats,
+                      void* stream);
+static bool strip_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("XV2_NO_STRIP");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int pick_bn(int kg) {
   for (int bn = 256; bn >= 16; bn -= 16)
     if (kg % bn == 0) return bn;
@@ -512,12 +533,16 @@ extern "C" int xv2_init(int device) {
 extern "C" int xv2_conv_tc(const xv2_tc_conv* q, const void* src0, const void* src1, const void* w,
                            const float* bias, void* out, double* stats, void* stream) {
   XV2_REQUIRE(q && src0 && w && out, "conv_tc: null argument");
-  if (stats) {
-    set_error("conv_tc: fused statistics epilogue not enabled in this build");
-    return XV2_EUNSUPPORTED;
-  }
   int rc = ensure_init();
   if (rc) return rc;
+  if (!bias && strip_enabled()) {
+    rc = conv_strip_launch(q, src0, src1, w, out, stats, stream);
+    if (rc != XV2_EUNSUPPORTED) return rc;
+  }
+  if (stats) {
+    set_error("conv_tc: fused statistics epilogue is not available for this shape");
+    return XV2_EUNSUPPORTED;
+  }
   const int groups = q->groups < 1 ? 1 : q->groups;
   const int ld0 = q->ld0 ? q->ld0 : q->c0, ld1 = q->ld1 ? q->ld1 : q->c1;
   const int ctot = q->c0 + q->c1;

@@ -48,7 +48,7 @@ class SplAtConv2d(nn.Module):
         self.fc2 = nn.Conv2d(inter, channels * 2, 1)
 
     def forward(self, x):
-        y = ops.batch_norm_act(run_conv(self.conv, x), self.bn0, ACT_RELU)
+        y = ops.conv_bn_act(x, self.conv, self.bn0, ACT_RELU)
         return ops.split_attention(y, self.fc1, self.bn1, self.fc2)
 
 
@@ -69,7 +69,7 @@ class SplAtBottleneck(nn.Module):
             self.downsample = None
 
     def forward(self, x):
-        out = ops.batch_norm_act(run_conv(self.conv1, x), self.bn1, ACT_RELU)
+        out = ops.conv_bn_act(x, self.conv1, self.bn1, ACT_RELU)
         out = self.conv2(out)
         if self.avd_stride:
             out = ops.avg_pool2d(out, 3, self.avd_stride, 1)
@@ -77,9 +77,9 @@ class SplAtBottleneck(nn.Module):
         if self.downsample is not None:
             if self.down_pool > 1:
                 res = ops.avg_pool2d(res, self.down_pool, self.down_pool, 0, ceil_mode=True, count_include_pad=False)
-            res = ops.batch_norm_act(run_conv(_sub(self.downsample, "1"), res), _sub(self.downsample, "2"), ACT_NONE)
+            res = ops.conv_bn_act(res, _sub(self.downsample, "1"), _sub(self.downsample, "2"), ACT_NONE)
         # bn3 + residual add + relu in one apply pass
-        return ops.batch_norm_act(run_conv(self.conv3, out), self.bn3, ACT_RELU, residual=res)
+        return ops.conv_bn_act(out, self.conv3, self.bn3, ACT_RELU, residual=res)
 
 
 class _BlockList(nn.Module):
@@ -110,9 +110,9 @@ class ResNeStStem(nn.Module):
 
     def forward(self, x):
         s = _sub(self, "0")
-        x = ops.batch_norm_act(run_conv(_sub(s, "0"), x), _sub(s, "1"), ACT_RELU)
-        x = ops.batch_norm_act(run_conv(_sub(s, "3"), x), _sub(s, "4"), ACT_RELU)
-        return ops.batch_norm_act(run_conv(_sub(s, "6"), x), _sub(self, "1"), ACT_RELU)
+        x = ops.conv_bn_act(x, _sub(s, "0"), _sub(s, "1"), ACT_RELU)
+        x = ops.conv_bn_act(x, _sub(s, "3"), _sub(s, "4"), ACT_RELU)
+        return ops.conv_bn_act(x, _sub(s, "6"), _sub(self, "1"), ACT_RELU)
 
 
 class PooledStage(nn.Module):
@@ -182,12 +182,12 @@ class Bottleneck(nn.Module):
             self.downsample = None
 
     def forward(self, x):
-        out = ops.batch_norm_act(run_conv(self.conv1, x), self.bn1, ACT_RELU)
-        out = ops.batch_norm_act(run_conv(self.conv2, out), self.bn2, ACT_RELU)
+        out = ops.conv_bn_act(x, self.conv1, self.bn1, ACT_RELU)
+        out = ops.conv_bn_act(out, self.conv2, self.bn2, ACT_RELU)
         res = x
         if self.downsample is not None:
-            res = ops.batch_norm_act(run_conv(_sub(self.downsample, "0"), x), _sub(self.downsample, "1"), ACT_NONE)
-        return ops.batch_norm_act(run_conv(self.conv3, out), self.bn3, ACT_RELU, residual=res)
+            res = ops.conv_bn_act(x, _sub(self.downsample, "0"), _sub(self.downsample, "1"), ACT_NONE)
+        return ops.conv_bn_act(out, self.conv3, self.bn3, ACT_RELU, residual=res)
 
 
 class ResNetStem(nn.Module):
@@ -199,7 +199,7 @@ class ResNetStem(nn.Module):
         self.add_module("1", nn.BatchNorm2d(64))
 
     def forward(self, x):
-        return ops.batch_norm_act(run_conv(_sub(self, "0"), x), _sub(self, "1"), ACT_RELU)
+        return ops.conv_bn_act(x, _sub(self, "0"), _sub(self, "1"), ACT_RELU)
 
 
 def build_resnet(name, dilation, in_channels=3):

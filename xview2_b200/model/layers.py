@@ -39,7 +39,7 @@ class ConvLayer(nn.Module):
 
     def forward(self, inputs, second=None):
         """`second`: optional tensor concatenated after `inputs` on channels without materialising the cat."""
-        return ops.batch_norm_act(run_conv(self.conv, inputs, second), self.batch_norm, ACT_LRELU)
+        return ops.conv_bn_act(inputs, self.conv, self.batch_norm, ACT_LRELU, x2=second)
 
 
 class ConvBlock(nn.Module):
@@ -63,7 +63,7 @@ class AttentionLayer(nn.Module):
         self.batch_norm = nn.BatchNorm2d(out_channels, affine=True)
 
     def forward(self, inputs, act=ACT_NONE, residual=None):
-        return ops.batch_norm_act(run_conv(self.conv, inputs), self.batch_norm, act, residual)
+        return ops.conv_bn_act(inputs, self.conv, self.batch_norm, act, residual=residual)
 
 
 class ConvTranspose(nn.Module):

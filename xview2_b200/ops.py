@@ -103,7 +103,15 @@ class _Conv2d(torch.autograd.Function):
     """nn.Conv2d (layers.py:92,71; encoder convs unet.py:52) with an optional second source concatenated on channels."""
 
     @staticmethod
-    def forward(ctx, x, x2, weight, bias, stride, pad, dil, groups):
+    def forward(ctx, x, x2, weight, bias, stride, pad, dil, groups, want_stats=False):
+        out, stats = _Conv2d._forward(ctx, x, x2, weight, bias, stride, pad, dil, groups, want_stats)
+        if stats is None:
+            stats = torch.empty(0, dtype=torch.float64, device=out.device)
+        ctx.mark_non_differentiable(stats)
+        return out, stats
+
+    @staticmethod
+    def _forward(ctx, x, x2, weight, bias, stride, pad, dil, groups, want_stats):
         _require_cuda(x)
         x = nhwc(x)
         n, c0, h, w = x.shape
@@ -124,16 +132,21 @@ class _Conv2d(torch.autograd.Function):
             p = TcConv(n, h, w, c0, c1, 0, 0, k, r, s, pad, dil, groups, 0, BF16, 0)
             lib.note_work(2.0 * n * h * w * k * cg * r * s, 2.0 * n * h * w * (c0 + c1 + k) + 2.0 * k * cg * r * s,
                           f"fwd n{n} {h}x{w} c{c0}+{c1} k{k} {r}x{s} g{groups}")
+            if want_stats:  # BN statistics fused into the conv epilogue (shapes served by the strip kernel)
+                stats = torch.zeros(2 * k, dtype=torch.float64, device=x.device)
+                rc = call("xv2_conv_tc", p, ptr(x), ptr(x2), ptr(wp), ptr(bias), ptr(out), ptr(stats), allow_unsupported=True)
+                if rc == 0:
+                    return out, stats
             rc = call("xv2_conv_tc", p, ptr(x), ptr(x2), ptr(wp), ptr(bias), ptr(out), None, allow_unsupported=True)
             if rc == 0:
-                return out
+                return out, None
         src = x if x2 is None else torch.cat((x, x2), 1)  # SIMT path only: plumbing copy
         src = nhwc(src)
         wp = pack_weight(weight, 0, x.dtype, groups)
-        return _conv_gather(src, wp, bias, n, h, w, c0 + c1, oh, ow, k, r, s, stride, pad, dil, 1, groups, x.dtype)
+        return _conv_gather(src, wp, bias, n, h, w, c0 + c1, oh, ow, k, r, s, stride, pad, dil, 1, groups, x.dtype), None
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dstats=None):
         x, x2, weight = ctx.saved_tensors
         stride, pad, dil, groups, c0, c1 = ctx.cfg
         dy = nhwc(dy)
@@ -194,7 +207,7 @@ class _Conv2d(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = torch.zeros(k, dtype=torch.float32, device=x.device)
             _colsum(dy, db)
-        return dx, dx2, dw, db, None, None, None, None
+        return dx, dx2, dw, db, None, None, None, None, None
 
 
 def _colsum(t, out):
@@ -208,7 +221,14 @@ def _colsum(t, out):
 
 
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, x2=None):
-    return _Conv2d.apply(x, x2, weight, bias, stride, padding, dilation, groups)
+    return _Conv2d.apply(x, x2, weight, bias, stride, padding, dilation, groups, False)[0]
+
+
+def conv2d_stats(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, x2=None):
+    """Convolution that also returns the fp64 [2k] (sum, sum of squares) of its rounded outputs when the kernel could
+    fuse them into its epilogue (else None): feeds batch_norm_act(..., stats=...)."""
+    out, stats = _Conv2d.apply(x, x2, weight, bias, stride, padding, dilation, groups, True)
+    return out, (stats if stats.numel() else None)
 
 
 class _ConvT2x2(torch.autograd.Function):
@@ -282,7 +302,7 @@ class _BatchNormAct(torch.autograd.Function):
     """nn.BatchNorm2d [+ residual add] [+ ReLU / LeakyReLU(0.01)] in one apply pass (layers.py:93-94, unet.py:52)."""
 
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, training, momentum, eps, act):
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, training, momentum, eps, act, stats=None):
         _require_cuda(x)
         x = nhwc(x)
         n, c, h, w = x.shape
@@ -295,8 +315,9 @@ class _BatchNormAct(torch.autograd.Function):
         if training:
             if pixels <= 1:
                 raise ValueError("Expected more than 1 value per channel when training")  # torch's own BN check
-            stats = torch.zeros(2 * c, dtype=torch.float64, device=dev)
-            call("xv2_bn_stats", ptr(x), pixels, c, dtype_code(x), ptr(stats))
+            if stats is None:
+                stats = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+                call("xv2_bn_stats", ptr(x), pixels, c, dtype_code(x), ptr(stats))
             call("xv2_bn_finalize", ptr(stats), pixels, c, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
                  float(momentum), float(eps), ptr(mean), ptr(invstd), ptr(scale), ptr(shift))
         else:
@@ -331,16 +352,27 @@ class _BatchNormAct(torch.autograd.Function):
         if not training:
             dgb[1].copy_(red[:c])
             dgb[0].copy_(red[c:])
-        return dx, dres, dgb[0], dgb[1], None, None, None, None, None, None
+        return dx, dres, dgb[0], dgb[1], None, None, None, None, None, None, None
 
 
-def batch_norm_act(x, bn, act=ACT_NONE, residual=None):
+def batch_norm_act(x, bn, act=ACT_NONE, residual=None, stats=None):
     """Applies the nn.BatchNorm2d module `bn` (its parameters / buffers / training flag) followed by `act`."""
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     use_batch = bn.training or not bn.track_running_stats
     return _BatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch,
-                               bn.momentum if bn.momentum is not None else 0.1, bn.eps, act)
+                               bn.momentum if bn.momentum is not None else 0.1, bn.eps, act, stats if use_batch else None)
+
+
+def conv_bn_act(x, conv, bn, act=ACT_NONE, x2=None, residual=None):
+    """conv -> BatchNorm -> activation (+ residual) for an nn.Conv2d / nn.BatchNorm2d parameter pair; in training the BN
+    statistics come out of the conv epilogue when the kernel supports it."""
+    args = (x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0], conv.groups, x2)
+    if bn.training or not bn.track_running_stats:
+        out, stats = conv2d_stats(*args)
+    else:
+        out, stats = conv2d(*args), None
+    return batch_norm_act(out, bn, act, residual, stats)
 
 
 # ---------------------------------------------------------------------------------------------------------------
