@@ -60,14 +60,14 @@ __device__ __forceinline__ Piece piece_at(long long lo, long long hi, int h, int
   return p;
 }
 
-template <int BK>
+template <int BK, int CHUNKS>
 __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constant__ StripParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t ROWB = BK * 2;                    // bytes per pixel row of a chunk = swizzle span
   constexpr uint32_t CHUNK_BYTES = kStripPitch * ROWB;  // multiple of the swizzle pattern (8 rows)
   const uint32_t tile_bytes = (uint32_t)p.bn * ROWB;   // one (tap, chunk) weight tile
-  const uint32_t w_bytes = 9u * p.chunks * tile_bytes;
-  const uint32_t slot_bytes = (uint32_t)p.chunks * CHUNK_BYTES;
+  const uint32_t w_bytes = 9u * CHUNKS * tile_bytes;
+  const uint32_t slot_bytes = (uint32_t)CHUNKS * CHUNK_BYTES;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t ring0 = base + ((w_bytes + 1023u) & ~1023u);
   const uint32_t bar_base = ring0 + p.ring * slot_bytes;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.map_a0);
     tma_prefetch_desc(&p.map_b);
-    if (p.chunks > p.chunks0) tma_prefetch_desc(&p.map_a1);
+    if (CHUNKS > p.chunks0) tma_prefetch_desc(&p.map_a1);
     for (int s = 0; s < p.ring; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    uint32_t g = 0;
+    uint32_t slot = 0, phase = 0;
     int cur_wset = -1;
     for (long long lo = lo0; lo < hi0;) {
       const Piece pc = piece_at(lo, hi0, p.h, p.wtiles, p.n);
@@ -116,32 +116,43 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
       const int grp = pc.wset / p.n_tiles, nt = pc.wset - grp * p.n_tiles;
       if (pc.wset != cur_wset) {
         // every MMA that reads the resident weights has completed once all row slots have been released
-        for (uint32_t j = 0; j < R; ++j) mbar_wait(empty0 + 8 * ((g + j) % R), (((g + j) / R) & 1) ^ 1);
+        uint32_t s2 = slot, p2 = phase;
+        for (uint32_t j = 0; j < R; ++j) {
+          mbar_wait(empty0 + 8 * s2, p2 ^ 1);
+          if (++s2 == R) { s2 = 0; p2 ^= 1; }
+        }
         mbar_expect_tx(wfull, w_bytes);
         for (int t = 0; t < 9; ++t)
-          for (int ch = 0; ch < p.chunks; ++ch)
-            tma_load_2d(base + (uint32_t)(t * p.chunks + ch) * tile_bytes, &p.map_b, wfull, t * p.cg + ch * BK,
+          for (int ch = 0; ch < CHUNKS; ++ch)
+            tma_load_2d(base + (uint32_t)(t * CHUNKS + ch) * tile_bytes, &p.map_b, wfull, t * p.cg + ch * BK,
                         grp * p.kg + nt * p.bn);
         cur_wset = pc.wset;
       }
-      for (int row = pc.ha - 1; row <= pc.hb; ++row, ++g) {
-        const uint32_t slot = g % R;
-        mbar_wait(empty0 + 8 * slot, ((g / R) & 1) ^ 1);
+      for (int row = pc.ha - 1; row <= pc.hb; ++row) {
+        mbar_wait(empty0 + 8 * slot, phase ^ 1);
         const uint32_t fb = full0 + 8 * slot;
-        mbar_expect_tx(fb, (uint32_t)p.chunks * kStripHalo * ROWB);
+        mbar_expect_tx(fb, (uint32_t)CHUNKS * kStripHalo * ROWB);
         const uint32_t dst = ring0 + slot * slot_bytes;
-        for (int ch = 0; ch < p.chunks; ++ch) {
+#pragma unroll
+        for (int ch = 0; ch < CHUNKS; ++ch) {
           if (ch < p.chunks0)
             tma_load_4d(dst + ch * CHUNK_BYTES, &p.map_a0, fb, grp * p.cg + ch * BK, pc.wt * kStripPix - 1, row, pc.img);
           else
             tma_load_4d(dst + ch * CHUNK_BYTES, &p.map_a1, fb, (ch - p.chunks0) * BK, pc.wt * kStripPix - 1, row, pc.img);
         }
+        if (++slot == R) { slot = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The WHOLE warp walks the loop (addresses stay warp-uniform, no per-MMA waterfall); one elected lane issues.
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.bn, 0, 0);
-    uint32_t g = 0, acc = 0, acc_phase = 0, wphase = 0;
+    const uint64_t dproto = make_smem_desc(0, 16, 8 * ROWB, ROWB);
+    const uint32_t d_hi = (uint32_t)(dproto >> 32), d_lo = (uint32_t)dproto;
+    const uint32_t a_lo0 = d_lo + (ring0 >> 4), b_lo0 = d_lo + (base >> 4);
+    const uint32_t slot16 = slot_bytes >> 4, tile16 = tile_bytes >> 4;
+    uint32_t sa = 0, pa = 0;  // ring iterator of the oldest live input row (slot, phase)
+    uint32_t acc = 0, acc_phase = 0, wphase = 0;
     int cur_wset = -1;
     for (long long lo = lo0; lo < hi0;) {
       const Piece pc = piece_at(lo, hi0, p.h, p.wtiles, p.n);
@@ -152,38 +163,50 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
         wphase ^= 1;
         cur_wset = pc.wset;
       }
-      mbar_wait(full0 + 8 * (g % R), (g / R) & 1);
-      mbar_wait(full0 + 8 * ((g + 1) % R), ((g + 1) / R) & 1);
+      uint32_t sb = sa + 1, pb = pa;
+      if (sb == R) { sb = 0; pb ^= 1; }
+      uint32_t sc = sb + 1, pcph = pb;
+      if (sc == R) { sc = 0; pcph ^= 1; }
+      mbar_wait(full0 + 8 * sa, pa);
+      mbar_wait(full0 + 8 * sb, pb);
       for (int i = 0; i < nrows; ++i) {
-        mbar_wait(full0 + 8 * ((g + i + 2) % R), ((g + i + 2) / R) & 1);
+        mbar_wait(full0 + 8 * sc, pcph);
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * (tmem_cols >> 1);
-        uint32_t accum = 0;
-#pragma unroll 1
-        for (int r = 0; r < 3; ++r) {
-          const uint32_t row_base = ring0 + ((g + i + r) % R) * slot_bytes;
-#pragma unroll 1
-          for (int s = 0; s < 3; ++s) {
-            for (int ch = 0; ch < p.chunks; ++ch) {
-              const uint64_t ad = make_smem_desc(row_base + ch * CHUNK_BYTES + s * ROWB, 16, 8 * ROWB, ROWB);
-              const uint64_t bd = make_smem_desc(base + (uint32_t)((r * 3 + s) * p.chunks + ch) * tile_bytes, 16, 8 * ROWB, ROWB);
+        if (elect_one()) {
+          const uint32_t rows_lo[3] = {a_lo0 + sa * slot16, a_lo0 + sb * slot16, a_lo0 + sc * slot16};
+          uint32_t b_lo = b_lo0;
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                umma_bf16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, accum);
-                accum = 1;
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+#pragma unroll
+              for (int ch = 0; ch < CHUNKS; ++ch) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16_lohi(d, rows_lo[r] + ((ch * CHUNK_BYTES + s * ROWB + k * 32) >> 4), d_hi, b_lo + 2 * k, d_hi, idesc,
+                                 (uint32_t)((r | s | ch | k) != 0));
+                b_lo += tile16;
               }
             }
           }
+          umma_commit(tfull0 + 8 * acc);
+          umma_commit(empty0 + 8 * sa);  // the oldest input row is not needed by later output rows
         }
-        umma_commit(tfull0 + 8 * acc);
-        umma_commit(empty0 + 8 * ((g + i) % R));  // input row ha-1+i is not needed by later output rows
+        __syncwarp();
+        sa = sb; pa = pb;
+        sb = sc; pb = pcph;
+        if (++sc == R) { sc = 0; pcph ^= 1; }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      umma_commit(empty0 + 8 * ((g + nrows) % R));
-      umma_commit(empty0 + 8 * ((g + nrows + 1) % R));
-      g += nrows + 2;
+      if (elect_one()) {
+        umma_commit(empty0 + 8 * sa);
+        umma_commit(empty0 + 8 * sb);
+      }
+      __syncwarp();
+      sa = sc; pa = pcph;
     }
   } else if (warp >= 2 && warp < 2 + epi_warps) {
     // ===================== epilogue =====================
@@ -331,13 +354,15 @@ int conv_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, 
   long long grid = tc_num_sms();
   if (grid > p.rows_total / 16) grid = p.rows_total / 16 > 0 ? p.rows_total / 16 : 1;
   cudaError_t e;
-  if (bk == 64) {
-    e = cudaFuncSetAttribute(conv_strip_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_strip_kernel<64><<<(unsigned)grid, 320, smem, as_stream(stream)>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(conv_strip_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_strip_kernel<32><<<(unsigned)grid, 320, smem, as_stream(stream)>>>(p);
-  }
+#define XV2_STRIP_LAUNCH(BKV, CH)                                                                                        \
+  do {                                                                                                                   \
+    e = cudaFuncSetAttribute(conv_strip_kernel<BKV, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    if (e == cudaSuccess) conv_strip_kernel<BKV, CH><<<(unsigned)grid, 320, smem, as_stream(stream)>>>(p);               \
+  } while (0)
+  if (bk == 32) XV2_STRIP_LAUNCH(32, 1);
+  else if (chunks == 1) XV2_STRIP_LAUNCH(64, 1);
+  else XV2_STRIP_LAUNCH(64, 2);
+#undef XV2_STRIP_LAUNCH
   if (e != cudaSuccess) {
     set_error("conv_strip: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     return XV2_ECUDA;
