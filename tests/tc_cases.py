@@ -29,6 +29,10 @@ CASES = {
     "strip_cat_64_64_k64_w128": ("conv", 2, 64, 64, 48, 128, 64, 3, 1, 1),
     "strip_g2_c64_k128_w128": ("conv", 2, 64, 0, 40, 128, 128, 3, 1, 2),
     "strip_g2_c128_k256_w128": ("conv", 1, 128, 0, 33, 128, 256, 3, 1, 2),
+    # strip weight-gradient shapes: narrow images, k blocks of 128, two sources with 32-channel chunks
+    "wg_c96_k256_w32": ("conv", 2, 96, 0, 20, 32, 256, 3, 1, 1),
+    "wg_cat_32_64_k128_w64": ("conv", 2, 32, 64, 24, 64, 128, 3, 1, 1),
+    "wg_g2_c64_k256_w16": ("conv", 3, 64, 0, 16, 16, 256, 3, 1, 2),
     "convt_c128_k64": ("convt", 2, 128, 0, 16, 16, 64, 2, 1, 1),
     "convt_c64_k32_w64": ("convt", 1, 64, 0, 8, 64, 32, 2, 1, 1),
     "convt_c2048_k512": ("convt", 1, 2048, 0, 16, 8, 512, 2, 1, 1),

@@ -132,32 +132,42 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       const int img = t2 / p.tiles_h;
       const int h0 = thi * p.th, w0 = twi * p.tw;
       const int brow = g * p.kg + n_tile * p.bn;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const int tr = tap / p.tap_s, ts = tap - tr * p.tap_s;
-        for (int kb = 0; kb < kb_per_tap; ++kb) {
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t sa = base + stage * stage_bytes, sb = sa + A_BYTES;
-          const uint32_t fb = full0 + 8 * stage;
-          mbar_expect_tx(fb, stage_bytes);
-          if (p.gather2x2) {
-            tma_load_5d(sa, &p.map_a0, fb, kb * BK, ts, w0, tr, img * p.h + h0);
-          } else if (kb < p.kb0) {
-            tma_load_4d(sa, &p.map_a0, fb, g * p.cg + kb * BK, w0 + ts * p.dil - p.pad, h0 + tr * p.dil - p.pad, img);
-          } else {
-            tma_load_4d(sa, &p.map_a1, fb, (kb - p.kb0) * BK, w0 + ts * p.dil - p.pad, h0 + tr * p.dil - p.pad, img);
-          }
-          tma_load_2d(sb, &p.map_b, fb, (tap * kb_per_tap + kb) * BK, brow);
-          if (++stage == (uint32_t)p.stages) {
-            stage = 0;
-            phase ^= 1;
+      int bcol = 0;
+      const int tap_r = p.taps / p.tap_s;
+      for (int tr = 0; tr < tap_r; ++tr) {
+        const int hc = h0 + tr * p.dil - p.pad;
+        for (int ts = 0; ts < p.tap_s; ++ts) {
+          const int wc = w0 + ts * p.dil - p.pad;
+          for (int kb = 0; kb < kb_per_tap; ++kb, bcol += BK) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t sa = base + stage * stage_bytes, sb = sa + A_BYTES;
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_expect_tx(fb, stage_bytes);
+            if (p.gather2x2) {
+              tma_load_5d(sa, &p.map_a0, fb, kb * BK, ts, w0, tr, img * p.h + h0);
+            } else if (kb < p.kb0) {
+              tma_load_4d(sa, &p.map_a0, fb, g * p.cg + kb * BK, wc, hc, img);
+            } else {
+              tma_load_4d(sa, &p.map_a1, fb, (kb - p.kb0) * BK, wc, hc, img);
+            }
+            tma_load_2d(sb, &p.map_b, fb, bcol, brow);
+            if (++stage == (uint32_t)p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // the whole warp walks the loop (warp-uniform addresses), one elected lane issues the MMAs and commits
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.bn, 0, 0);
+    const uint64_t dproto = make_smem_desc(0, 16, SBO, SWZ);
+    const uint32_t d_hi = (uint32_t)(dproto >> 32), d_lo = (uint32_t)dproto;
+    const uint32_t stage16 = stage_bytes >> 4;
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    uint32_t a_lo = d_lo + (base >> 4);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
@@ -165,18 +175,22 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t sa = base + stage * stage_bytes, sb = sa + A_BYTES;
-        const uint64_t ad = make_smem_desc(sa, 16, SBO, SWZ), bd = make_smem_desc(sb, 16, SBO, SWZ);
+        if (elect_one()) {
+          const uint32_t b_lo = a_lo + (A_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_bf16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-        umma_commit(empty0 + 8 * stage);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_lohi(d, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(empty0 + 8 * stage);
+          if (kb == num_kb - 1) umma_commit(tfull0 + 8 * acc);
+        }
+        __syncwarp();
+        a_lo += stage16;
         if (++stage == (uint32_t)p.stages) {
           stage = 0;
           phase ^= 1;
+          a_lo = d_lo + (base >> 4);
         }
       }
-      umma_commit(tfull0 + 8 * acc);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -358,28 +372,35 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         phase ^= 1;
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
+    // whole warp in the loop (warp-uniform addresses); one elected lane issues
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.bn, 1, 1);
     const uint32_t swz_x = p.atom_x * 2, swz_y = p.atom_y * 2;
+    // MN-major: LBO = stride between MN atoms (one TMA box), SBO = stride between 8-pixel (K) groups
+    const uint64_t ap = make_smem_desc(0, ax_bytes, 8 * swz_x, swz_x), bp = make_smem_desc(0, ay_bytes, 8 * swz_y, swz_y);
+    const uint32_t a_hi = (uint32_t)(ap >> 32), b_hi = (uint32_t)(bp >> 32);
+    const uint32_t kx = (16 * swz_x) >> 4, ky = (16 * swz_y) >> 4;  // 16 pixel rows per UMMA K step
     uint32_t stage = 0, phase = 0;
     for (int pt = pt_begin; pt < pt_end; ++pt) {
       mbar_wait(full0 + 8 * stage, phase);
       tc_fence_after();
-      const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
-      // MN-major: LBO = stride between MN atoms (one TMA box), SBO = stride between 8-pixel (K) groups
-      const uint64_t ad = make_smem_desc(sa, ax_bytes, 8 * swz_x, swz_x);
-      const uint64_t bd = make_smem_desc(sb, ay_bytes, 8 * swz_y, swz_y);
+      if (elect_one()) {
+        const uint32_t sa = base + stage * stage_bytes;
+        const uint32_t a_lo = (uint32_t)ap + (sa >> 4), b_lo = (uint32_t)bp + ((sa + a_bytes) >> 4);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)  // 128 pixels = 8 UMMA K-steps of 16 rows
-        umma_bf16(tmem_base, ad + (uint64_t)((k * 16 * swz_x) >> 4), bd + (uint64_t)((k * 16 * swz_y) >> 4), idesc,
-                  (uint32_t)((pt != pt_begin) | (k != 0)));
-      umma_commit(empty0 + 8 * stage);
+        for (int k = 0; k < 8; ++k)  // 128 pixels = 8 UMMA K-steps of 16 rows
+          umma_bf16_lohi(tmem_base, a_lo + k * kx, a_hi, b_lo + k * ky, b_hi, idesc, (uint32_t)((pt != pt_begin) | (k != 0)));
+        umma_commit(empty0 + 8 * stage);
+        if (pt == pt_end - 1) umma_commit(tfull0);
+      }
+      __syncwarp();
       if (++stage == (uint32_t)p.stages) {
         stage = 0;
         phase ^= 1;
       }
     }
-    umma_commit(tfull0);
+    if (pt_end <= pt_begin && elect_one()) mbar_arrive(tfull0);
+    __syncwarp();
   } else if (warp >= 2) {
     const int q = warp & 3;
     const int m = q * 32 + lane;
@@ -495,6 +516,8 @@ int strip_encode_weight(CUtensorMap* m, const void* ptr, long long rows, long lo
 int tc_num_sms() { return g_num_sms; }
 int conv_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, const void* w, void* out, double* stats,
                       void* stream);
+int wgrad_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, const void* dout, int lddo, float* dw,
+                       void* stream);
 static bool strip_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -636,6 +659,10 @@ extern "C" int xv2_wgrad_tc(const xv2_tc_conv* q, const void* src0, const void* 
   XV2_REQUIRE(q && src0 && dout && dw, "wgrad_tc: null argument");
   int rc = ensure_init();
   if (rc) return rc;
+  if (strip_enabled()) {
+    rc = wgrad_strip_launch(q, src0, src1, dout, lddo, dw, stream);
+    if (rc != XV2_EUNSUPPORTED) return rc;
+  }
   const int groups = q->groups < 1 ? 1 : q->groups;
   const bool convt = q->convt == 1;
   int th, tw;
