@@ -135,6 +135,45 @@ def test_batch_norm_act(dtype, training, act, with_res, c):
         assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == 1
 
 
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("act,with_res,c,hw", [(2, False, 32, (100, 83)), (1, True, 256, (50, 41)), (0, False, 2048, (17, 16))])
+def test_batch_norm_stream(training, act, with_res, c, hw):
+    """Large bf16 tensors take the shared-memory-staged streaming kernels (bn_stream.cu); ragged last chunk included."""
+    ops = _ops()
+    dtype = torch.bfloat16
+    bn = torch.nn.BatchNorm2d(c).cuda()
+    bn.weight.data = rnd(c, seed=5) * 0.2 + 1
+    bn.bias.data = rnd(c, seed=6) * 0.2
+    bn.running_mean.data = rnd(c, seed=7) * 0.1
+    bn.running_var.data = rnd(c, seed=8).abs() + 0.5
+    bn.train(training)
+    ref = torch.nn.BatchNorm2d(c).cuda()
+    ref.load_state_dict(bn.state_dict())
+    ref.train(training)
+    h, w = hw
+    x = rnd(4, c, h, w, dtype=dtype, seed=1).contiguous(memory_format=CL).requires_grad_(True)
+    assert x.numel() >= 1 << 20
+    res = rnd(4, c, h, w, dtype=dtype, seed=2).contiguous(memory_format=CL).requires_grad_(True) if with_res else None
+    y = ops.batch_norm_act(x, bn, act, res)
+    gy = rnd(*y.shape, dtype=dtype, seed=3).contiguous(memory_format=CL)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    rr = res.detach().float().requires_grad_(True) if with_res else None
+    u = ref(xr)
+    if with_res:
+        u = u + rr
+    yr = u if act == 0 else (F.relu(u) if act == 1 else F.leaky_relu(u, 0.01))
+    yr.backward(gy.float())
+    t = tol(dtype)
+    assert rel(y, yr) < t
+    assert rel(x.grad, xr.grad) < t * 2
+    assert rel(bn.weight.grad, ref.weight.grad) < t * 2 and rel(bn.bias.grad, ref.bias.grad) < t * 2
+    if with_res:
+        assert rel(res.grad, rr.grad) < t
+    if training:
+        assert rel(bn.running_mean, ref.running_mean) < 1e-3 and rel(bn.running_var, ref.running_var) < 1e-3
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_pools(dtype):
     ops = _ops()

@@ -20,6 +20,10 @@ for s in $STAGES; do
         -k regex:conv_tc_kernel -s 40 -c 3 -f -o gpurun_out/prof_conv python tools/layer_profile.py --ncu > gpurun_out/ncu_conv.log 2>&1; tail -3 gpurun_out/ncu_conv.log ;;
     ncu_strip) timeout 1200 $NCU --set full --clock-control none --import-source on --profile-from-start off \
         -k regex:conv_strip_kernel -c 8 -f -o gpurun_out/prof_strip python tools/layer_profile.py --ncu > gpurun_out/ncu_strip.log 2>&1; tail -3 gpurun_out/ncu_strip.log ;;
+    ncu_bn) timeout 1200 $NCU --set full --clock-control none --import-source on --profile-from-start off \
+        -k regex:"bn_bwd" -c 8 -f -o gpurun_out/prof_bnbwd python tools/layer_profile.py --ncu > gpurun_out/ncu_bn.log 2>&1; tail -2 gpurun_out/ncu_bn.log
+        timeout 1200 $NCU --set full --clock-control none --import-source on --profile-from-start off \
+        -k regex:"bn_apply|bn_stats" -c 8 -f -o gpurun_out/prof_bnfwd python tools/layer_profile.py --ncu > gpurun_out/ncu_bn2.log 2>&1; tail -2 gpurun_out/ncu_bn2.log ;;
     ncu_wgrad) timeout 1200 $NCU --set full --clock-control none --import-source on --profile-from-start off \
         -k regex:wgrad_tc_kernel -s 20 -c 3 -f -o gpurun_out/prof_wgrad python tools/layer_profile.py --ncu > gpurun_out/ncu_wgrad.log 2>&1; tail -3 gpurun_out/ncu_wgrad.log ;;
   esac

@@ -374,6 +374,18 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const T* __restric
 
 }  // namespace xv2
 
+namespace xv2 {
+bool bn_stream_ok(int64_t pixels, int c, int dtype);
+int bn_stream_stats(const void* x, int64_t pixels, int c, double* stats, void* stream);
+int bn_stream_apply(const void* x, const void* res, void* y, int64_t pixels, int c, const float* scale, const float* shift,
+                    int act, void* stream);
+int bn_stream_bwd_reduce(const void* dy, const void* x, const void* res, int64_t pixels, int c, const float* scale,
+                         const float* shift, const float* mean, const float* invstd, int act, double* red, void* stream);
+int bn_stream_bwd_apply(const void* dy, const void* x, const void* res, void* dx, void* dres, int64_t pixels, int c,
+                        const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma,
+                        int act, const double* red, int64_t count, float* dgamma, float* dbeta, void* stream);
+}  // namespace xv2
+
 using namespace xv2;
 
 #define XV2_DISPATCH_VEC(T, vec, KERNEL, ...)                 \
@@ -384,6 +396,7 @@ using namespace xv2;
 
 extern "C" int xv2_bn_stats(const void* x, int64_t pixels, int32_t c, int32_t dtype, double* stats, void* stream) {
   XV2_REQUIRE(c > 0 && pixels > 0, "bn_stats: empty tensor");
+  if (bn_stream_ok(pixels, c, dtype)) return bn_stream_stats(x, pixels, c, stats, stream);
   const int vec = pick_vec(c, dtype);
   RowMap m = make_rowmap(c, vec);
   int blocks = pick_blocks(pixels, m, 32);
@@ -416,6 +429,7 @@ extern "C" int xv2_bn_eval_coeffs(int32_t c, const float* gamma, const float* be
 extern "C" int xv2_bn_apply(const void* x, const void* residual, void* y, int64_t pixels, int32_t c, int32_t dtype,
                             const float* scale, const float* shift, int32_t act, void* stream) {
   XV2_REQUIRE(c > 0 && pixels > 0, "bn_apply: empty tensor");
+  if (bn_stream_ok(pixels, c, dtype)) return bn_stream_apply(x, residual, y, pixels, c, scale, shift, act, stream);
   const int vec = pick_vec(c, dtype);
   RowMap m = make_rowmap(c, vec);
   int blocks = pick_blocks(pixels, m, 8);
@@ -430,6 +444,8 @@ extern "C" int xv2_bn_bwd_reduce(const void* dy, const void* x, const void* resi
                                  int32_t dtype, const float* scale, const float* shift, const float* mean,
                                  const float* invstd, int32_t act, double* red, void* stream) {
   XV2_REQUIRE(c > 0 && pixels > 0, "bn_bwd_reduce: empty tensor");
+  if (bn_stream_ok(pixels, c, dtype))
+    return bn_stream_bwd_reduce(dy, x, residual, pixels, c, scale, shift, mean, invstd, act, red, stream);
   const int vec = pick_vec(c, dtype);
   RowMap m = make_rowmap(c, vec);
   int blocks = pick_blocks(pixels, m, 32);
@@ -447,6 +463,9 @@ extern "C" int xv2_bn_bwd_apply(const void* dy, const void* x, const void* resid
                                 const float* mean, const float* invstd, const float* gamma, int32_t act,
                                 const double* red, int64_t count, float* dgamma, float* dbeta, void* stream) {
   XV2_REQUIRE(c > 0 && pixels > 0, "bn_bwd_apply: empty tensor");
+  if (bn_stream_ok(pixels, c, dtype))
+    return bn_stream_bwd_apply(dy, x, residual, dx, dres, pixels, c, scale, shift, mean, invstd, gamma, act, red, count, dgamma,
+                               dbeta, stream);
   const int vec = pick_vec(c, dtype);
   RowMap m = make_rowmap(c, vec);
   int blocks = pick_blocks(pixels, m, 8);
