@@ -1,0 +1,228 @@
+"""CPU tests of the host side: CLI surface, tile sharding, loader datasets / augmentation, Noam schedule, flat gradient
+all-reduce over gloo (world size 2), C-ABI symbol export.  No CUDA compute is called."""
+import argparse
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C ABI
+# ---------------------------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    from xview2_b200 import build, lib
+
+    build.build()
+    handle = lib.load()
+    header = open(os.path.join(ROOT, "include", "xv2.h")).read()
+    declared = set(re.findall(r"\b(xv2_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/xv2.h but not exported"
+    assert set(lib.exported_symbols()) == declared
+
+
+def test_ops_refuse_cpu_tensors():
+    from xview2_b200 import lib, ops
+
+    with pytest.raises(lib.Xv2Error):
+        ops.conv2d(torch.zeros(1, 32, 8, 8), torch.zeros(32, 32, 3, 3), None, 1, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CLI (reference main.py:29-53 + plt.py:185-233)
+# ---------------------------------------------------------------------------------------------------------------
+def test_cli_flags_and_defaults_match_reference():
+    sys.path.insert(0, ROOT)
+    import main as cli
+
+    a = cli.build_parser().parse_args(["--type", "pre"])
+    expect = dict(exec_mode="train", data="/data", results="/results", gpus=1, num_workers=8, batch_size=16, val_batch_size=13,
+                  precision=16, epochs=250, patience=100, ckpt=None, logname="logs", ckpt_pre=None, type="pre", seed=1,
+                  optimizer="adamw", dmg_model="siamese", encoder="resnest200", loss_str="focal+dice", use_scheduler=False,
+                  warmup=1, init_lr=1e-4, final_lr=1e-4, lr=3e-4, weight_decay=0, momentum=0.9, dilation=1, tta=False,
+                  ppm=False, aspp=False, no_skip=False, deep_supervision=False, attention=False, autoaugment=False,
+                  interpolate=False, dec_interp=False)
+    for k, v in expect.items():
+        assert getattr(a, k) == v, (k, getattr(a, k), v)
+    assert len(vars(a)) == len(expect)
+    assert cli.build_parser().parse_args(["--type", "post", "--precision", "bf16"]).precision == "bf16"
+    with pytest.raises(SystemExit):
+        cli.build_parser().parse_args(["--type", "both"])
+
+
+def test_transplant_encoder_key_rules():
+    import main as cli
+
+    class Fake:
+        def __init__(self, keys):
+            self.sd = {k: torch.zeros(2) for k in keys}
+
+        def state_dict(self):
+            return self.sd
+
+    pre = {"model.unet.enc_l1.0.0.weight": torch.ones(2), "model.unet.dec_l1.x": torch.ones(2)}
+    m = Fake(["model.unet.enc_l1.0.0.weight", "model.unet.dec_l1.x"])
+    assert cli.transplant_encoder(m, pre, "siamese") == 1
+    assert m.sd["model.unet.enc_l1.0.0.weight"].sum() == 2 and m.sd["model.unet.dec_l1.x"].sum() == 0
+    m = Fake(["model.enc_l1.0.0.weight"])
+    assert cli.transplant_encoder(m, pre, "siameseEnc") == 1
+    m = Fake(["model.unet_pre.enc_l1.0.0.weight", "model.unet_post.enc_l1.0.0.weight"])
+    assert cli.transplant_encoder(m, pre, "parallel") == 2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sharding = DistributedSampler semantics
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,world,shuffle", [(10, 2, False), (11, 4, True), (7, 8, False), (16, 1, True)])
+def test_shard_indices_match_distributed_sampler(n, world, shuffle):
+    from torch.utils.data.distributed import DistributedSampler
+
+    from xview2_b200.data_loading.pytorch_loader import shard_indices
+
+    seen = []
+    for rank in range(world):
+        ours = shard_indices(n, rank, world, shuffle, seed=3, epoch=2, drop_last=False, batch_size=1)
+        if world > 1:
+            ref = DistributedSampler(list(range(n)), num_replicas=world, rank=rank, shuffle=shuffle, seed=3)
+            ref.set_epoch(2)
+            assert ours == list(iter(ref))
+        seen += ours
+    assert set(seen) == set(range(n))  # every tile is visited; padding repeats only wrap around
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# datasets + augmentation on synthetic PNG tiles
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture()
+def tile_dir(tmp_path):
+    import cv2
+
+    rng = np.random.default_rng(0)
+    for split in ("train", "test", "holdout"):
+        os.makedirs(tmp_path / split / "images")
+        os.makedirs(tmp_path / split / "targets")
+        for i in range(3):
+            for kind in ("pre", "post"):
+                img = rng.integers(0, 256, (1024, 1024, 3), dtype=np.uint8)
+                lbl = np.zeros((1024, 1024), np.uint8)
+                lbl[300:420, 500:640] = 1 + (i % 4 if kind == "post" else 0)
+                cv2.imwrite(str(tmp_path / split / "images" / f"tile{i}_{kind}_disaster.png"), img)
+                cv2.imwrite(str(tmp_path / split / "targets" / f"tile{i}_{kind}_disaster_target.png"), lbl)
+    return tmp_path
+
+
+def test_datasets_return_decoded_uint8_tiles(tile_dir):
+    import cv2
+
+    from xview2_b200.data_loading.pytorch_loader import TestDataset, TrainPostDataset, TrainPreDataset
+
+    ds = TestDataset(str(tile_dir / "holdout"), "post", False)
+    assert len(ds) == 3
+    item = ds[1]
+    ref = cv2.imread(str(tile_dir / "holdout" / "images" / "tile1_pre_disaster.png"))  # BGR, as the reference reads it
+    assert item["tiles"].dtype == np.uint8 and item["tiles"].shape == (1024, 1024, 3) and np.array_equal(item["tiles"], ref)
+    assert item["tiles_post"].shape == (1024, 1024, 3) and item["mask"].shape == (1024, 1024) and item["mask"].max() == 2
+    pre = TrainPreDataset(str(tile_dir / "train"), "pre", False)
+    a, b = pre[0], pre[0]
+    assert a["tiles"].shape == (512, 512, 3) and a["mask"].shape == (512, 512)
+    assert a["mask"].any(), "CropNonEmptyMaskIfExists must keep building pixels in the crop"
+    assert np.array_equal(a["tiles"], b["tiles"]), "augmentation is a pure function of (seed, index, epoch)"
+    post = TrainPostDataset(str(tile_dir / "train"), "post", False)
+    item = post[2]
+    assert item["tiles"].shape == item["tiles_post"].shape == (512, 512, 3) and item["mask"].any()
+    with pytest.raises(NotImplementedError):
+        TrainPreDataset(str(tile_dir / "train"), "pre", True)
+
+
+def test_normalize_constants_match_albumentations():
+    """A.Normalize() (pytorch_loader.py:63): (x - 255*mean) * (1 / (255*std)) with the ImageNet constants, applied to BGR
+    channel POSITIONS exactly as the reference does (cv2 loads BGR)."""
+    from oracle import functional as OF
+
+    x = np.arange(0, 256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, 2)
+    out = np.asarray(OF.normalize_tile(x))
+    mean = np.array([0.485, 0.456, 0.406], np.float32) * 255
+    rstd = 1 / (np.array([0.229, 0.224, 0.225], np.float32) * 255)
+    ref = (x.astype(np.float32) - mean) * rstd
+    assert np.allclose(out, np.transpose(ref, (2, 0, 1)), atol=1e-6)
+
+
+def test_brightness_contrast_and_noise_are_uint8_safe():
+    import random
+
+    from xview2_b200.data_loading.pytorch_loader import TrainAugment
+
+    img = np.full((64, 64, 6), 250, np.uint8)
+    rng = random.Random(1)
+    for _ in range(50):
+        out = TrainAugment._brightness_contrast(rng, img)
+        assert out.dtype == np.uint8 and out.shape == img.shape
+    out = TrainAugment._noise(random.Random(5), np.random.default_rng(5), img)
+    assert out.dtype == np.uint8
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Noam schedule (utils/scheduler.py:45-59)
+# ---------------------------------------------------------------------------------------------------------------
+def test_noam_lr_warmup_then_decay():
+    from xview2_b200.utils.scheduler import NoamLR
+
+    class Opt:
+        param_groups = [{"lr": 0.0}]
+
+    sch = NoamLR(Opt(), warmup_epochs=1, total_epochs=3, steps_per_epoch=10, init_lr=1e-4, max_lr=1e-3, final_lr=1e-5)
+    lrs = []
+    for _ in range(30):
+        sch.step()
+        lrs.append(Opt.param_groups[0]["lr"])
+    assert abs(lrs[9] - 1e-3) < 1e-9 and all(b > a for a, b in zip(lrs[:9], lrs[1:10]))
+    assert all(b < a for a, b in zip(lrs[10:], lrs[11:])) and abs(lrs[-1] - 1e-5) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# data-parallel plumbing over gloo, world size 2: ONE all-reduce of the flat gradient buffer + rank-0 broadcast
+# ---------------------------------------------------------------------------------------------------------------
+def _dp_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xview2_b200.data_loading.pytorch_loader import shard_indices
+    from xview2_b200.optim import FlatParams
+
+    torch.manual_seed(100 + rank)  # different initial weights per rank: the broadcast must make them equal
+    net = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3, bias=False), torch.nn.BatchNorm2d(8), torch.nn.Conv2d(8, 2, 1))
+    flat = FlatParams(net)
+    flat.broadcast_params(0)
+    ref = flat.data.clone()
+    dist.broadcast(ref, 0)
+    same_params = bool(torch.equal(ref, flat.data))
+    # tiles sharded over ranks: the per-rank "gradient" is the sum of its tile indices
+    tiles = shard_indices(10, rank, world, False, 1, 0, False, 1)
+    for p in net.parameters():
+        p.grad.fill_(float(sum(tiles)))
+    n = flat.all_reduce_grads()
+    views_alias_flat = all(p.grad.data_ptr() >= flat.grad.data_ptr() for p in net.parameters())
+    out[rank] = (same_params, n, float(flat.grad[0]), views_alias_flat)
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29600 + os.getpid() % 200
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    assert len(out) == 2
+    for rank in range(2):
+        same, n, g0, alias = out[rank]
+        assert same and n == 2 and alias
+        assert g0 == float(sum(range(10)))  # SUM over ranks of disjoint tile shards = sum over all tiles

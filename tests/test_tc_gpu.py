@@ -13,22 +13,28 @@ def test_tc_conv(name):
         assert val < 2e-2, (name, errs)
 
 
-@pytest.mark.parametrize("shape", [(2, 32, 0, 64, 256, 32, 1), (2, 64, 64, 24, 128, 64, 1), (1, 128, 0, 40, 128, 256, 2)])
+@pytest.mark.parametrize("shape", [(2, 32, 0, 64, 256, 32, 1, 3), (2, 64, 64, 24, 128, 64, 1, 3), (1, 128, 0, 40, 128, 256, 2, 3),
+                                   (2, 64, 0, 32, 32, 256, 1, 1), (2, 256, 0, 16, 16, 96, 1, 3), (3, 128, 64, 24, 64, 512, 1, 3),
+                                   (2, 128, 0, 16, 16, 256, 2, 3), (2, 512, 0, 8, 16, 2048, 1, 1)])
 def test_conv_stats_epilogue(shape):
-    """BN statistics fused into the strip-conv epilogue == sums over the stored (bf16-rounded) outputs."""
+    """BN statistics fused into the conv epilogues (strip and tile kernels) == sums over the stored (bf16-rounded) outputs."""
     import torch
 
     from xview2_b200 import ops
-    n, c0, c1, h, w, k, groups = shape
+    n, c0, c1, h, w, k, groups, r = shape
     g = torch.Generator().manual_seed(5)
     cl = torch.channels_last
     x = torch.randn(n, c0, h, w, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=cl)
     x2 = torch.randn(n, c1, h, w, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=cl) if c1 else None
     cg = (c0 + c1) // groups
-    wt = (torch.randn(k, cg, 3, 3, generator=g) * (2.0 / (9 * cg)) ** 0.5).cuda().contiguous(memory_format=cl)
-    out, stats = ops.conv2d_stats(x, wt, None, 1, 1, 1, groups, x2)
-    assert stats is not None, "strip kernel declined a strip shape"
+    wt = (torch.randn(k, cg, r, r, generator=g) * (2.0 / (r * r * cg)) ** 0.5).cuda().contiguous(memory_format=cl)
+    out, stats = ops.conv2d_stats(x, wt, None, 1, r // 2, 1, groups, x2)
+    assert stats is not None, "tensor-core kernels declined the fused statistics"
     o = out.double()
     ref = torch.cat((o.sum((0, 2, 3)), (o * o).sum((0, 2, 3))))
+    import torch.nn.functional as F
+    src = x.float() if x2 is None else torch.cat((x.float(), x2.float()), 1)
+    yr = F.conv2d(src, wt.to(torch.bfloat16).float(), None, 1, r // 2, 1, groups)
+    assert float((out.float() - yr).abs().max() / yr.abs().max()) < 2e-2
     err = float((stats - ref).abs().max() / ref.abs().max())
     assert err < 1e-5, err

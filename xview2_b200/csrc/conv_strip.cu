@@ -221,7 +221,10 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
       lo += nrows;
       const int grp = pc.wset / p.n_tiles, nt = pc.wset - grp * p.n_tiles;
       const int co0 = grp * p.kg + nt * p.bn;
-      float ssum0 = 0.f, ssq0 = 0.f, ssum1 = 0.f, ssq1 = 0.f;  // lane j: channel (block*32 + j) after the transpose-reduce
+      float ssum1 = 0.f, ssq1 = 0.f;  // second column block: lane j holds channel (32 + j) after each row's transpose-reduce
+      float rs[32], rq[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rs[j] = rq[j] = 0.f;
       for (int i = 0; i < nrows; ++i) {
         const long long pix = ((long long)pc.img * p.h + (pc.ha + i)) * p.w + pc.wt * kStripPix + m;
         mbar_wait(tfull0 + 8 * acc, acc_phase);
@@ -247,25 +250,19 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
             *reinterpret_cast<uint4*>(o + j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
           if (p.stats) {
-            float sq[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
-            // transpose-reduce: after the 5 steps lane j holds the sum over the warp's 32 pixels of column j
-#pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) {
-              const bool up = (lane & s) != 0;
-#pragma unroll
-              for (int j = 0; j < s; ++j) {
-                const float keep = up ? f[j + s] : f[j], send = up ? f[j] : f[j + s];
-                f[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-                const float keep2 = up ? sq[j + s] : sq[j], send2 = up ? sq[j] : sq[j + s];
-                sq[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, s);
-              }
-            }
             if (bi == 0) {
-              ssum0 += f[0];
-              ssq0 += sq[0];
+              // first column block: per-thread running sums over the whole piece, transposed once at its end
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                rs[j] += f[j];
+                rq[j] = fmaf(f[j], f[j], rq[j]);
+              }
             } else {
+              float sq[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+              warp_transpose_sum(f, lane);
+              warp_transpose_sum(sq, lane);
               ssum1 += f[0];
               ssq1 += sq[0];
             }
@@ -278,10 +275,12 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
         if (acc == 0) acc_phase ^= 1;
       }
       if (p.stats) {
+        warp_transpose_sum(rs, lane);
+        warp_transpose_sum(rq, lane);
         int bi = 0;
         for (int c0 = cgrp * 32; c0 < p.bn; c0 += cgroups * 32, ++bi) {
-          atomicAdd(p.stats + co0 + c0 + lane, (double)(bi == 0 ? ssum0 : ssum1));
-          atomicAdd(p.stats + p.k_total + co0 + c0 + lane, (double)(bi == 0 ? ssq0 : ssq1));
+          atomicAdd(p.stats + co0 + c0 + lane, (double)(bi == 0 ? rs[0] : ssum1));
+          atomicAdd(p.stats + p.k_total + co0 + c0 + lane, (double)(bi == 0 ? rq[0] : ssq1));
         }
       }
     }

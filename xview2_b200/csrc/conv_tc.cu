@@ -73,11 +73,16 @@ struct alignas(64) TcParams {
   int out_f32;
   void* out;
   const float* bias;
+  // TMA-store epilogue (bf16 output, N tile a multiple of 32): staged through swizzled shared memory
+  CUtensorMap map_out;
+  int tma_store;           // 0: direct register -> global stores
+  int store_c;             // channels per staged block (64 -> 128B swizzle, 32 -> 64B swizzle)
+  double* stats;           // optional fp64 [2 * k_total]: BN sum / sum of squares of the rounded outputs
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int BK>
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = 128 * BK * 2;
   constexpr uint32_t SWZ = BK * 2;          // swizzle span = bytes per operand row
@@ -88,19 +93,27 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   const uint32_t bar_base = base + p.stages * stage_bytes;
   const uint32_t full0 = bar_base, empty0 = bar_base + 64, tfull0 = bar_base + 128, tempty0 = bar_base + 144;
   const uint32_t tmem_slot = bar_base + 160;
+  const uint32_t stage_out0 = (bar_base + 256 + 1023u) & ~1023u;  // 2 x 16 KB output staging (one per epilogue half)
+  const uint32_t stats_sm = stage_out0 + 2 * 16384;                // float [2 * k_total] when p.stats
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int epi_warps = p.tma_store ? 8 : 4;
 
+  if (p.stats) {
+    for (int i = threadIdx.x; i < 2 * p.k_total; i += blockDim.x)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(stats_sm + 4 * i), "f"(0.f) : "memory");
+  }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.map_a0);
     tma_prefetch_desc(&p.map_b);
     if (p.kb1 > 0) tma_prefetch_desc(&p.map_a1);
+    if (p.tma_store) tma_prefetch_desc(&p.map_out);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 4);
+      mbar_init(tempty0 + 8 * a, epi_warps);
     }
     fence_barrier_init();
   }
@@ -194,8 +207,96 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp >= 2) {
-    // ===================== epilogue =====================
+  } else if (warp >= 2 && p.tma_store) {
+    // ===================== epilogue (TMA store): 2 halves x 4 warps; half h owns staged blocks h, h+2, ... =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;
+    const int m = q * 32 + lane;       // row of the tile (pixel)
+    const bool issuer = (q == ((2 + 4 * half) & 3)) && lane == 0;  // lane 0 of the half's first warp
+    const uint32_t sbuf = stage_out0 + half * 16384;
+    const int nblocks = p.bn / p.store_c;
+    const uint32_t rowb = (uint32_t)p.store_c * 2;
+    const uint32_t row_addr = sbuf + m * rowb;
+    const uint32_t swz = p.store_c == 64 ? (uint32_t)(m & 7) : (uint32_t)((m >> 1) & 3);
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int t = tile / p.n_tiles;
+      const int g = t % p.groups;
+      const int m_tile = t / p.groups;
+      const int twi = m_tile % p.tiles_w;
+      const int t2 = m_tile / p.tiles_w;
+      const int thi = t2 % p.tiles_h;
+      const int img = t2 / p.tiles_h;
+      int co0, tap2 = 0;
+      if (p.convt) {
+        const int nglob = n_tile * p.bn;
+        tap2 = nglob / p.k_total;
+        co0 = nglob - tap2 * p.k_total;
+      } else {
+        co0 = g * p.kg + n_tile * p.bn;
+      }
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+      for (int sb = half; sb < nblocks; sb += 2) {
+        if (issuer) bulk_wait_read0();  // the previous TMA store out of this half's buffer has been read
+        named_bar_sync(1 + half, 128);
+        for (int part = 0; part < p.store_c; part += 32) {
+          const int col = sb * p.store_c + part;
+          uint32_t v[32];
+          tmem_ld_32x32(trow + col, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float a = __uint_as_float(v[j + 2 * i]), b = __uint_as_float(v[j + 2 * i + 1]);
+              if (p.bias) {
+                a += p.bias[co0 + col + j + 2 * i];
+                b += p.bias[co0 + col + j + 2 * i + 1];
+              }
+              __nv_bfloat162 hp = __floats2bfloat162_rn(a, b);
+              w4[i] = *reinterpret_cast<uint32_t*>(&hp);
+              f[j + 2 * i] = __uint_as_float(w4[i] << 16);
+              f[j + 2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u);
+            }
+            const uint32_t chunk = (uint32_t)((part + j) >> 3);  // 16-byte chunk within the staged row
+            st_shared_v4(row_addr + ((chunk ^ swz) << 4), w4[0], w4[1], w4[2], w4[3]);
+          }
+          if (p.stats) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+            warp_transpose_sum(f, lane);
+            warp_transpose_sum(sq, lane);
+            const uint32_t sa = stats_sm + 4 * (co0 + col + lane);
+            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa), "f"(f[0]) : "memory");
+            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa + 4 * p.k_total), "f"(sq[0]) : "memory");
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync(1 + half, 128);
+        if (issuer) {
+          const int cc = co0 + sb * p.store_c;
+          if (p.convt)
+            tma_store_5d(&p.map_out, sbuf, cc, tap2 & 1, twi * p.tw, tap2 >> 1, img * p.h + thi * p.th);
+          else
+            tma_store_2d(&p.map_out, sbuf, cc, ((img * p.h + thi * p.th) * p.w + twi * p.tw));
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (issuer) bulk_wait_all();
+  } else if (warp >= 2 && warp < 6) {
+    // ===================== epilogue (direct stores: fp32 output / odd N tiles) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;
     const int th_i = m >> p.tw_log2, tw_i = m & (p.tw - 1);
@@ -264,6 +365,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (p.stats) {
+    for (int i = threadIdx.x; i < 2 * p.k_total; i += blockDim.x) {
+      float v;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stats_sm + 4 * i));
+      if (v != 0.f) atomicAdd(p.stats + i, (double)v);
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -527,6 +635,38 @@ static bool strip_enabled() {
   return v == 1;
 }
 
+// output tile maps for the TMA-store epilogue
+static int encode_out_map(CUtensorMap* m, void* ptr, long long pixels, int k, int ldo, int box_c) {
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)pixels};
+  cuuint64_t strides[1] = {(cuuint64_t)ldo * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_c, 128};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(output %lld x %d ld %d) failed: %d", pixels, k, ldo, (int)r);
+    return XV2_ECUDA;
+  }
+  return XV2_OK;
+}
+// transposed conv: output (n, 2h, 2w, k) viewed as {k, 2 (kw), w, 2 (kh), h*n}
+static int encode_out_shuffle_map(CUtensorMap* m, void* ptr, int n, int h, int w, int k, int ldo, int box_c, int tw, int th) {
+  cuuint64_t dims[5] = {(cuuint64_t)k, 2, (cuuint64_t)w, 2, (cuuint64_t)h * n};
+  cuuint64_t strides[4] = {(cuuint64_t)ldo * 2, (cuuint64_t)2 * ldo * 2, (cuuint64_t)2 * w * ldo * 2,
+                           (cuuint64_t)4 * w * ldo * 2};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, 1, (cuuint32_t)tw, 1, (cuuint32_t)th};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(pixel-shuffle output) failed: %d", (int)r);
+    return XV2_ECUDA;
+  }
+  return XV2_OK;
+}
+
 static int pick_bn(int kg) {
   for (int bn = 256; bn >= 16; bn -= 16)
     if (kg % bn == 0) return bn;
@@ -561,10 +701,6 @@ extern "C" int xv2_conv_tc(const xv2_tc_conv* q, const void* src0, const void* s
   if (!bias && strip_enabled()) {
     rc = conv_strip_launch(q, src0, src1, w, out, stats, stream);
     if (rc != XV2_EUNSUPPORTED) return rc;
-  }
-  if (stats) {
-    set_error("conv_tc: fused statistics epilogue is not available for this shape");
-    return XV2_EUNSUPPORTED;
   }
   const int groups = q->groups < 1 ? 1 : q->groups;
   const int ld0 = q->ld0 ? q->ld0 : q->c0, ld1 = q->ld1 ? q->ld1 : q->c1;
@@ -621,8 +757,23 @@ extern "C" int xv2_conv_tc(const xv2_tc_conv* q, const void* src0, const void* s
   p.cg = cg;
   p.kg = kg;
   p.bn = bn;
+  const bool tma_store = q->out_dtype == XV2_BF16 && bn % 32 == 0;
+  if (stats && (!tma_store || convt || q->k > 2048)) {
+    set_error("conv_tc: fused statistics epilogue is not available for this shape");
+    return XV2_EUNSUPPORTED;
+  }
+  uint32_t extra = 0;
+  if (tma_store) {
+    p.tma_store = 1;
+    p.store_c = (bn % 64 == 0 && bn > 64) ? 64 : 32;
+    rc = convt ? encode_out_shuffle_map(&p.map_out, out, q->n, q->h, q->w, q->k, ldo, p.store_c, tw, th)
+               : encode_out_map(&p.map_out, out, (long long)q->n * q->h * q->w, q->k, ldo, p.store_c);
+    if (rc) return rc;
+    extra = 1024 + 2 * 16384 + (stats ? 8u * q->k : 0u);
+    p.stats = stats;
+  }
   const uint32_t stage_bytes = 128u * bk * 2 + (uint32_t)bn * bk * 2;
-  int stages = (int)(kSmemBudget / stage_bytes);
+  int stages = (int)((kSmemBudget - extra) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
   p.gather2x2 = gather ? 1 : 0;
@@ -634,17 +785,17 @@ extern "C" int xv2_conv_tc(const xv2_tc_conv* q, const void* src0, const void* s
   p.out_f32 = q->out_dtype == XV2_F32;
   p.out = out;
   p.bias = bias;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + extra;
   const long long total = (long long)p.m_tiles * p.n_tiles * groups;
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
   cudaStream_t st = as_stream(stream);
   cudaError_t e;
   if (bk == 64) {
     e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_tc_kernel<64><<<grid, 192, smem, st>>>(p);
+    if (e == cudaSuccess) conv_tc_kernel<64><<<grid, 320, smem, st>>>(p);
   } else {
     e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_tc_kernel<32><<<grid, 192, smem, st>>>(p);
+    if (e == cudaSuccess) conv_tc_kernel<32><<<grid, 320, smem, st>>>(p);
   }
   if (e != cudaSuccess) {
     set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -134,9 +134,11 @@ class _Conv2d(torch.autograd.Function):
                           f"fwd n{n} {h}x{w} c{c0}+{c1} k{k} {r}x{s} g{groups}")
             if want_stats:  # BN statistics fused into the conv epilogue (shapes served by the strip kernel)
                 stats = torch.zeros(2 * k, dtype=torch.float64, device=x.device)
+                work = lib._work
                 rc = call("xv2_conv_tc", p, ptr(x), ptr(x2), ptr(wp), ptr(bias), ptr(out), ptr(stats), allow_unsupported=True)
                 if rc == 0:
                     return out, stats
+                lib._work = work
             rc = call("xv2_conv_tc", p, ptr(x), ptr(x2), ptr(wp), ptr(bias), ptr(out), None, allow_unsupported=True)
             if rc == 0:
                 return out, None
