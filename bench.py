@@ -273,14 +273,18 @@ def run_ours(a):
         name, d = top
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath):  # ncu dram__bytes_read + write per launch of this entry point's kernels (tools/make_traffic.py)
             with open(tpath) as f:
-                traffic = json.load(f).get(name)
+                traffic = (json.load(f).get(name) or {}).get("dram_bytes_per_launch")
         if d["flops"] > 0:
             ach = d["flops"] / d["ms"] / 1e9  # TFLOP/s over all launches of this entry point in the step
             roof = {"kernel": name, "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tensor"], "unit": "TFLOP/s",
                     "frac": round(ach / peaks["tensor"], 4), "traffic": traffic, "peak_source": peaks["src"] + " (sustained bf16)",
-                    "launches": d["calls"], "avg_launch_ms": round(d["ms"] / d["calls"], 4), "share_of_step": round(d["ms"] / total, 4)}
+                    "launches": d["calls"], "avg_launch_ms": round(d["ms"] / d["calls"], 4), "share_of_step": round(d["ms"] / total, 4),
+                    "algorithmic_gflop_per_launch": round(d["flops"] / d["calls"] / 1e9, 2),
+                    "algorithmic_bytes_per_launch": round(d["bytes"] / d["calls"]),
+                    "hbm_gbs": round(d["bytes"] / d["ms"] / 1e6, 1), "hbm_frac": round(d["bytes"] / d["ms"] / 1e6 / peaks["hbm"], 4),
+                    "note": "the conv entry point runs on the ridge: both the tensor and the HBM fraction are reported"}
         else:
             ach = d["bytes"] / d["ms"] / 1e6  # GB/s
             roof = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s",

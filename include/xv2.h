@@ -69,6 +69,15 @@ int xv2_conv_gather_simt(const xv2_conv_geom* g, const void* src, const void* w,
  * sum_{n,oh,ow} dout[n,oh,ow,k] * src[n,ih,iw,g*Cg+c]; same index rule as above.  dout has geom.out dims, dtype `dtype`. */
 int xv2_conv_wgrad_simt(const xv2_conv_geom* g, const void* src, const void* dout, float* dw, void* stream);
 
+/* ResNeSt deep-stem first convolution (unet.py:52 -> conv1[0]): 3x3 stride 2 pad 1, 3 input channels, k = 32 | 64, bf16 NHWC
+ * in / out, fp32 weights [k][3][3][3]; and its weight gradient (fp32, ACCUMULATED: caller zero-fills). */
+int xv2_stem_conv_fwd(const void* x, const float* w, void* y, int32_t n, int32_t h, int32_t wd, int32_t k, void* stream);
+int xv2_stem_conv_wgrad(const void* x, const void* dy, float* dw, int32_t n, int32_t h, int32_t wd, int32_t k, void* stream);
+/* Fully connected layers of split attention on [n][c] fp32 vectors (SplAtConv2d fc1 / fc2, 1x1 convs on a 1x1 image):
+ * y[n][k] = b[k] + sum_c x[n][c] w[k][c];   dw[k][c] = sum_n dy[n][k] x[n][c], db[k] = sum_n dy[n][k] (both WRITTEN). */
+int xv2_fc_fwd(const float* x, const float* w, const float* b, float* y, int32_t n, int32_t c, int32_t k, void* stream);
+int xv2_fc_wgrad(const float* x, const float* dy, float* dw, float* db, int32_t n, int32_t c, int32_t k, void* stream);
+
 /* Sum over pixels of a [pixels][k] tensor -> fp32 [k] (bias gradient of the 1x1 output head, layers.py:180). */
 int xv2_colsum(const void* x, int64_t pixels, int32_t k, int32_t dtype, float* out, void* stream);
 
@@ -78,6 +87,14 @@ int xv2_colsum(const void* x, int64_t pixels, int32_t k, int32_t dtype, float* o
  * mode 2: dst[r][s][b][a] (transposed-conv GEMM rows for xv2_conv_tc convt=1; groups must be 1). */
 int xv2_pack_weight(const float* src, void* dst, int32_t a, int32_t r, int32_t s, int32_t b, int32_t groups,
                     int32_t mode, int32_t dst_dtype, void* stream);
+
+/* Every packed copy of the model in ONE launch (after the optimizer step rewrote the masters): `jobs` is a DEVICE array. */
+typedef struct xv2_pack_job {
+  const void* src;          /* fp32 master [a][r][s][b] */
+  void* dst;                /* packed copy */
+  int32_t a, r, s, b, groups, mode, dst_dtype, pad_;
+} xv2_pack_job;
+int xv2_pack_weights_batched(const xv2_pack_job* jobs, int32_t njobs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 + TMEM + TMA) implicit-GEMM convolution, bf16 in / fp32 accumulate.
@@ -127,6 +144,11 @@ int xv2_bn_eval_coeffs(int32_t c, const float* gamma, const float* beta, const f
 /* y = act(scale*x + shift (+ residual)) */
 int xv2_bn_apply(const void* x, const void* residual, void* y, int64_t pixels, int32_t c, int32_t dtype,
                  const float* scale, const float* shift, int32_t act, void* stream);
+/* training forward in one call: finalize (as xv2_bn_finalize, coef = [4][c] mean | invstd | scale | shift, running statistics
+ * updated) + apply; on the streaming path the finalize step is folded into the apply kernel's prologue (no extra launch). */
+int xv2_bn_train_apply(const void* x, const void* residual, void* y, int64_t pixels, int32_t c, int32_t dtype,
+                       const double* stats, int64_t count, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float momentum, float eps, float* coef, int32_t act, void* stream);
 /* backward pass 1: through the activation (recomputed from x, scale, shift, residual) then the two BN reductions.
  * red (fp64 [2*c], accumulated; caller zero-fills) = (sum du, sum du * xhat).  */
 int xv2_bn_bwd_reduce(const void* dy, const void* x, const void* residual, int64_t pixels, int32_t c, int32_t dtype,

@@ -135,6 +135,23 @@ def test_batch_norm_act(dtype, training, act, with_res, c):
         assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == 1
 
 
+@pytest.mark.parametrize("k,hw", [(32, (64, 96)), (64, (33, 47))])
+def test_stem_conv_direct(k, hw):
+    """Cin = 3 stride-2 stem conv (ResNeSt conv1[0]) runs the direct kernel: forward + weight gradient vs torch fp32."""
+    ops = _ops()
+    h, w = hw
+    x = rnd(2, 3, h, w, dtype=torch.bfloat16, seed=1).contiguous(memory_format=CL)
+    wt = (rnd(k, 3, 3, 3, seed=2) * 0.3).contiguous(memory_format=CL).requires_grad_(True)
+    y = ops.conv2d(x, wt, None, 2, 1, 1, 1)
+    gy = rnd(*y.shape, dtype=torch.bfloat16, seed=3).contiguous(memory_format=CL)
+    y.backward(gy)
+    wr = wt.detach().clone().requires_grad_(True)
+    yr = F.conv2d(x.float(), wr, None, 2, 1)
+    yr.backward(gy.float())
+    assert y.shape == yr.shape
+    assert rel(y, yr) < 1e-2 and rel(wt.grad, wr.grad) < 1e-3
+
+
 @pytest.mark.parametrize("training", [True, False])
 @pytest.mark.parametrize("act,with_res,c,hw", [(2, False, 32, (100, 83)), (1, True, 256, (50, 41)), (0, False, 2048, (17, 16))])
 def test_batch_norm_stream(training, act, with_res, c, hw):

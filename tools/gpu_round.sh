@@ -24,8 +24,11 @@ for s in $STAGES; do
         -k regex:"bn_bwd" -c 8 -f -o gpurun_out/prof_bnbwd python tools/layer_profile.py --ncu > gpurun_out/ncu_bn.log 2>&1; tail -2 gpurun_out/ncu_bn.log
         timeout 1200 $NCU --set full --clock-control none --import-source on --profile-from-start off \
         -k regex:"bn_apply|bn_stats" -c 8 -f -o gpurun_out/prof_bnfwd python tools/layer_profile.py --ncu > gpurun_out/ncu_bn2.log 2>&1; tail -2 gpurun_out/ncu_bn2.log ;;
+    traffic) timeout 1500 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+        --profile-from-start off --csv --log-file gpurun_out/traffic.csv python tools/layer_profile.py --ncu > gpurun_out/traffic.log 2>&1; wc -l gpurun_out/traffic.csv ;;
+    bench2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench2.json 2> gpurun_out/bench2.err; tail -c 600 gpurun_out/bench2.json; tail -3 gpurun_out/bench2.err ;;
     ncu_wgrad) timeout 1200 $NCU --set full --clock-control none --import-source on --profile-from-start off \
-        -k regex:wgrad_tc_kernel -s 20 -c 3 -f -o gpurun_out/prof_wgrad python tools/layer_profile.py --ncu > gpurun_out/ncu_wgrad.log 2>&1; tail -3 gpurun_out/ncu_wgrad.log ;;
+        -k regex:wgrad_ -s 4 -c 6 -f -o gpurun_out/prof_wgrad python tools/layer_profile.py --ncu > gpurun_out/ncu_wgrad.log 2>&1; tail -3 gpurun_out/ncu_wgrad.log ;;
   esac
 done
 echo "=== done $(date +%T)"

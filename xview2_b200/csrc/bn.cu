@@ -381,6 +381,9 @@ int bn_stream_apply(const void* x, const void* res, void* y, int64_t pixels, int
                     int act, void* stream);
 int bn_stream_bwd_reduce(const void* dy, const void* x, const void* res, int64_t pixels, int c, const float* scale,
                          const float* shift, const float* mean, const float* invstd, int act, double* red, void* stream);
+int bn_stream_train_apply(const void* x, const void* res, void* y, int64_t pixels, int c, const double* stats, int64_t count,
+                          const float* gamma, const float* beta, float* rmean, float* rvar, float momentum, float eps,
+                          float* coef, int act, void* stream);
 int bn_stream_bwd_apply(const void* dy, const void* x, const void* res, void* dx, void* dres, int64_t pixels, int c,
                         const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma,
                         int act, const double* red, int64_t count, float* dgamma, float* dbeta, void* stream);
@@ -438,6 +441,20 @@ extern "C" int xv2_bn_apply(const void* x, const void* residual, void* y, int64_
                                                                          c, m, scale, shift, act)));
   XV2_LAUNCH_CHECK();
   return XV2_OK;
+}
+
+extern "C" int xv2_bn_train_apply(const void* x, const void* residual, void* y, int64_t pixels, int32_t c, int32_t dtype,
+                                  const double* stats, int64_t count, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, float momentum, float eps, float* coef,
+                                  int32_t act, void* stream) {
+  XV2_REQUIRE(c > 0 && pixels > 0 && count > 0 && stats && coef, "bn_train_apply: bad argument");
+  if (bn_stream_ok(pixels, c, dtype))
+    return bn_stream_train_apply(x, residual, y, pixels, c, stats, count, gamma, beta, running_mean, running_var, momentum, eps,
+                                 coef, act, stream);
+  int rc = xv2_bn_finalize(stats, count, c, gamma, beta, running_mean, running_var, momentum, eps, coef, coef + c, coef + 2 * c,
+                           coef + 3 * c, stream);
+  if (rc) return rc;
+  return xv2_bn_apply(x, residual, y, pixels, c, dtype, coef + 2 * c, coef + 3 * c, act, stream);
 }
 
 extern "C" int xv2_bn_bwd_reduce(const void* dy, const void* x, const void* residual, int64_t pixels, int32_t c,

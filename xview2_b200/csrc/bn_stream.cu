@@ -34,7 +34,29 @@ struct BnStreamParams {
   double* red_out;            // stats: (sum, sumsq);  bwd_reduce: (sum du, sum du*xhat)
   float inv_n;
   float *dgamma, *dbeta;
+  // BN_APPLY with the finalize step fused (training): coefficients come from `fin_stats` instead of scale / shift
+  const double* fin_stats;    // fp64 [2c] (sum, sum of squares) over fin_count values per channel, or null
+  const float *fin_gamma, *fin_beta;
+  float *fin_rmean, *fin_rvar, *fin_coef;  // running statistics (updated by block 0), coef = [4][c] mean|invstd|scale|shift
+  float fin_momentum, fin_eps;
+  long long fin_count;
 };
+
+// nn.BatchNorm2d training statistics of one channel (same arithmetic as bn_finalize_kernel in bn.cu)
+__device__ __forceinline__ void bn_finalize_channel(const BnStreamParams& p, int ch, float* mean, float* invstd, float* scale,
+                                                    float* shift, double* var_out) {
+  const double n = (double)p.fin_count;
+  const double mu = p.fin_stats[ch] / n;
+  double var = p.fin_stats[p.c + ch] / n - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)p.fin_eps));
+  const float g = p.fin_gamma ? p.fin_gamma[ch] : 1.f, b = p.fin_beta ? p.fin_beta[ch] : 0.f;
+  *mean = (float)mu;
+  *invstd = is;
+  *scale = g * is;
+  *shift = b - (float)mu * g * is;
+  *var_out = var;
+}
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -78,6 +100,24 @@ __global__ void __launch_bounds__(288, 2) bn_stream_kernel(const BnStreamParams 
     }
     fence_barrier_init();
   }
+  if (MODE == BN_APPLY && p.fin_stats != nullptr && blockIdx.x == 0) {
+    // fused finalize: block 0 publishes the saved coefficients and updates the running statistics
+    for (int i = tid; i < p.c; i += blockDim.x) {
+      float mean, invstd, scale, shift;
+      double var;
+      bn_finalize_channel(p, i, &mean, &invstd, &scale, &shift, &var);
+      p.fin_coef[i] = mean;
+      p.fin_coef[p.c + i] = invstd;
+      p.fin_coef[2 * p.c + i] = scale;
+      p.fin_coef[3 * p.c + i] = shift;
+      if (p.fin_rmean) {
+        const double n = (double)p.fin_count;
+        const double unbiased = p.fin_count > 1 ? var * n / (n - 1.0) : var;
+        p.fin_rmean[i] = (1.f - p.fin_momentum) * p.fin_rmean[i] + p.fin_momentum * mean;
+        p.fin_rvar[i] = (1.f - p.fin_momentum) * p.fin_rvar[i] + p.fin_momentum * (float)unbiased;
+      }
+    }
+  }
   if (MODE == BN_BWD_APPLY && blockIdx.x == 0 && p.red_in != nullptr && p.dgamma != nullptr) {
     for (int i = tid; i < p.c; i += blockDim.x) {
       p.dbeta[i] = (float)p.red_in[i];
@@ -114,7 +154,11 @@ __global__ void __launch_bounds__(288, 2) bn_stream_kernel(const BnStreamParams 
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     a1[i] = a2[i] = 0.f;
-    if (MODE != BN_STATS) {
+    if (MODE == BN_APPLY && p.fin_stats != nullptr) {
+      float mean, invstd;
+      double var;
+      bn_finalize_channel(p, cbase + i, &mean, &invstd, &sc[i], &sh[i], &var);
+    } else if (MODE != BN_STATS) {
       sc[i] = p.scale[cbase + i];
       sh[i] = p.shift[cbase + i];
     }
@@ -277,6 +321,29 @@ int bn_stream_apply(const void* x, const void* res, void* y, int64_t pixels, int
   p.n_in = res ? 2 : 1;
   p.scale = scale;
   p.shift = shift;
+  return launch_stream<BN_APPLY>(p, stream);
+}
+int bn_stream_train_apply(const void* x, const void* res, void* y, int64_t pixels, int c, const double* stats, int64_t count,
+                          const float* gamma, const float* beta, float* rmean, float* rvar, float momentum, float eps,
+                          float* coef, int act, void* stream) {
+  BnStreamParams p;
+  memset(&p, 0, sizeof(p));
+  p.in0 = (const __nv_bfloat16*)x;
+  p.in1 = (const __nv_bfloat16*)res;
+  p.out0 = (__nv_bfloat16*)y;
+  p.elems = pixels * c;
+  p.c = c;
+  p.act = act;
+  p.n_in = res ? 2 : 1;
+  p.fin_stats = stats;
+  p.fin_gamma = gamma;
+  p.fin_beta = beta;
+  p.fin_rmean = rmean;
+  p.fin_rvar = rvar;
+  p.fin_coef = coef;
+  p.fin_momentum = momentum;
+  p.fin_eps = eps;
+  p.fin_count = count;
   return launch_stream<BN_APPLY>(p, stream);
 }
 int bn_stream_bwd_reduce(const void* dy, const void* x, const void* res, int64_t pixels, int c, const float* scale,

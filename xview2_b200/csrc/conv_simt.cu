@@ -247,6 +247,45 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, TD* __restrict
   }
 }
 
+// one launch for every packed copy of the model: blockIdx.y selects the job, blockIdx.x strides over its elements
+template <typename TD>
+__device__ __forceinline__ void pack_job(const xv2_pack_job& j) {
+  const float* __restrict__ src = reinterpret_cast<const float*>(j.src);
+  TD* __restrict__ dst = reinterpret_cast<TD*>(j.dst);
+  const int a = j.a, r = j.r, s = j.s, b = j.b, mode = j.mode;
+  const long long total = (long long)a * r * s * b;
+  const int ag = a / j.groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long si;
+    if (mode == 0) {
+      si = i;
+    } else if (mode == 2) {
+      int ai = (int)(i % a);
+      long long t = i / a;
+      int bi = (int)(t % b);
+      t /= b;
+      int ss = (int)(t % s);
+      int rr = (int)(t / s);
+      si = (((long long)ai * r + rr) * s + ss) * b + bi;
+    } else {
+      int ai = (int)(i % ag);
+      long long t = i / ag;
+      int ss = (int)(t % s);
+      t /= s;
+      int rr = (int)(t % r);
+      int row = (int)(t / r);
+      int grp = row / b, bi = row - grp * b;
+      si = (((long long)(grp * ag + ai) * r + (r - 1 - rr)) * s + (s - 1 - ss)) * b + bi;
+    }
+    dst[i] = from_f<TD>(src[si]);
+  }
+}
+__global__ void pack_weights_batched_kernel(const xv2_pack_job* __restrict__ jobs) {
+  const xv2_pack_job j = jobs[blockIdx.y];
+  if (j.dst_dtype == XV2_BF16) pack_job<__nv_bfloat16>(j);
+  else pack_job<float>(j);
+}
+
 static int make_geom(const xv2_conv_geom* q, GatherGeom* g) {
   XV2_REQUIRE(q != nullptr, "null geometry");
   XV2_REQUIRE(q->groups >= 1 && q->c % q->groups == 0 && q->k % q->groups == 0, "channels %d/%d not divisible by groups %d",
@@ -346,6 +385,13 @@ extern "C" int xv2_pack_weight(const float* src, void* dst, int32_t a, int32_t r
   int blocks = (int)std::min<long long>(cdiv(total, 256), 8 * kNumSMs);
   XV2_DISPATCH_DTYPE(dst_dtype, T, (pack_weight_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(src, (T*)dst, a, r, s, b,
                                                                                                groups, mode)));
+  XV2_LAUNCH_CHECK();
+  return XV2_OK;
+}
+
+extern "C" int xv2_pack_weights_batched(const xv2_pack_job* jobs, int32_t njobs, void* stream) {
+  XV2_REQUIRE(jobs != nullptr && njobs > 0 && njobs <= 65535, "pack_weights_batched: bad job table");
+  pack_weights_batched_kernel<<<dim3(192, njobs), 256, 0, as_stream(stream)>>>(jobs);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }

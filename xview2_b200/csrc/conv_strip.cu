@@ -24,6 +24,7 @@ using namespace tc;
 int strip_encode_act(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int ld, int box_c, int box_w);
 int strip_encode_weight(CUtensorMap* m, const void* ptr, long long rows, long long kdim, int box_k, int box_rows);
 int tc_num_sms();
+int strip_encode_out(CUtensorMap* m, void* ptr, long long pixels, int k, int ldo, int box_c);
 
 constexpr int kStripPix = 128;               // output pixels per row tile (UMMA M)
 constexpr int kStripHalo = kStripPix + 2;    // input pixels fetched per row
@@ -31,7 +32,7 @@ constexpr int kStripPitch = 136;             // row pitch of a slot in pixels (m
 constexpr int kStripMaxRing = 12;
 
 struct alignas(64) StripParams {
-  CUtensorMap map_a0, map_a1, map_b;
+  CUtensorMap map_a0, map_a1, map_b, map_out;
   int n, h, w, wtiles;
   int groups, n_tiles;      // weight sets = groups * n_tiles
   int cg, kg, bn;           // in / out channels per group, N tile
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
   const uint32_t bar_base = ring0 + p.ring * slot_bytes;
   const uint32_t full0 = bar_base, empty0 = bar_base + 8 * kStripMaxRing, wfull = empty0 + 8 * kStripMaxRing;
   const uint32_t tfull0 = wfull + 8, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
+  const uint32_t stage_out0 = (bar_base + 512 + 1023u) & ~1023u;  // 2 x 8 KB output staging (one per column group)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int epi_warps = p.bn >= 64 ? 8 : 4;
   const uint32_t tmem_cols = p.bn <= 16 ? 32u : (p.bn <= 32 ? 64u : (p.bn <= 64 ? 128u : 256u));  // 2 accumulators
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.map_a0);
     tma_prefetch_desc(&p.map_b);
+    tma_prefetch_desc(&p.map_out);
     if (CHUNKS > p.chunks0) tma_prefetch_desc(&p.map_a1);
     for (int s = 0; s < p.ring; ++s) {
       mbar_init(full0 + 8 * s, 1);
@@ -214,6 +217,10 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
     const int cgrp = (warp - 2) >> 2;          // column group (0 | 1)
     const int cgroups = epi_warps >> 2;
     const int m = q * 32 + lane;               // pixel within the row tile
+    const bool issuer = q == 2 && lane == 0;   // lane 0 of the column group's first warp issues the TMA stores
+    const uint32_t sbuf = stage_out0 + cgrp * 8192;  // [128 pixels][32 channels] bf16, 64B-swizzled
+    const uint32_t row_addr = sbuf + m * 64;
+    const uint32_t swz = (uint32_t)((m >> 1) & 3);
     uint32_t acc = 0, acc_phase = 0;
     for (long long lo = lo0; lo < hi0;) {
       const Piece pc = piece_at(lo, hi0, p.h, p.wtiles, p.n);
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
 #pragma unroll
       for (int j = 0; j < 32; ++j) rs[j] = rq[j] = 0.f;
       for (int i = 0; i < nrows; ++i) {
-        const long long pix = ((long long)pc.img * p.h + (pc.ha + i)) * p.w + pc.wt * kStripPix + m;
+        const int pix0 = (pc.img * p.h + (pc.ha + i)) * p.w + pc.wt * kStripPix;
         mbar_wait(tfull0 + 8 * acc, acc_phase);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (tmem_cols >> 1);
@@ -235,8 +242,9 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
           uint32_t v[32];
           tmem_ld_32x32(trow + c0, v);
           tmem_ld_wait();
+          if (issuer) bulk_wait_read0();  // the previous TMA store out of this group's staging buffer has been read
+          named_bar_sync(1 + cgrp, 128);
           float f[32];
-          __nv_bfloat16* o = p.out + pix * p.ldo + co0 + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint32_t w4[4];
@@ -247,7 +255,13 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
               f[j + 2 * t] = __uint_as_float(w4[t] << 16);
               f[j + 2 * t + 1] = __uint_as_float(w4[t] & 0xffff0000u);
             }
-            *reinterpret_cast<uint4*>(o + j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            st_shared_v4(row_addr + ((((uint32_t)j >> 3) ^ swz) << 4), w4[0], w4[1], w4[2], w4[3]);
+          }
+          fence_proxy_async();
+          named_bar_sync(1 + cgrp, 128);
+          if (issuer) {
+            tma_store_2d(&p.map_out, sbuf, co0 + c0, pix0);
+            bulk_commit();
           }
           if (p.stats) {
             if (bi == 0) {
@@ -285,6 +299,7 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
       }
     }
   }
+  if (warp >= 2 && warp < 2 + epi_warps && (warp & 3) == 2 && lane == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -309,7 +324,7 @@ int conv_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, 
   const int bk = cg == 32 ? 32 : 64;
   const int chunks = cg / bk;
   const uint32_t rowb = bk * 2, chunk_bytes = kStripPitch * rowb, slot_bytes = chunks * chunk_bytes;
-  const uint32_t budget = 232448 - 1024 - 512;
+  const uint32_t budget = 232448 - 1024 - 512 - (1024 + 2 * 8192);  // minus the output staging buffers
   int bn = 0, ring = 0;
   for (int cand : {128, 64, 32}) {
     if (kg % cand) continue;
@@ -330,6 +345,7 @@ int conv_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, 
   int rc = strip_encode_act(&p.map_a0, src0, q->n, q->h, q->w, q->c0, ld0, bk, kStripHalo);
   if (!rc && q->c1) rc = strip_encode_act(&p.map_a1, src1, q->n, q->h, q->w, q->c1, ld1, bk, kStripHalo);
   if (!rc) rc = strip_encode_weight(&p.map_b, w, q->k, 9LL * cg, bk, bn);
+  if (!rc) rc = strip_encode_out(&p.map_out, out, (long long)q->n * q->h * q->w, q->k, ldo, 32);
   if (rc) return rc;
   p.n = q->n;
   p.h = q->h;
@@ -349,7 +365,7 @@ int conv_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, 
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.stats = stats;
   const uint32_t wb = ((9u * chunks * bn * rowb) + 1023u) & ~1023u;
-  const size_t smem = 1024 + wb + (size_t)ring * slot_bytes + 512;
+  const size_t smem = 1024 + wb + (size_t)ring * slot_bytes + 512 + 1024 + 2 * 8192;
   long long grid = tc_num_sms();
   if (grid > p.rows_total / 16) grid = p.rows_total / 16 > 0 ? p.rows_total / 16 : 1;
   cudaError_t e;

@@ -228,11 +228,11 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       const int t2 = m_tile / p.tiles_w;
       const int thi = t2 % p.tiles_h;
       const int img = t2 / p.tiles_h;
-      int co0, tap2 = 0;
-      if (p.convt) {
+      int co0, kh = 0;
+      if (p.convt) {  // N index = (kh, kw, k): a tile lies inside one kh; co0 indexes the contiguous (kw, k) row segment
         const int nglob = n_tile * p.bn;
-        tap2 = nglob / p.k_total;
-        co0 = nglob - tap2 * p.k_total;
+        kh = nglob / (2 * p.k_total);
+        co0 = nglob - kh * 2 * p.k_total;
       } else {
         co0 = g * p.kg + n_tile * p.bn;
       }
@@ -247,7 +247,6 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           uint32_t v[32];
           tmem_ld_32x32(trow + col, v);
           tmem_ld_wait();
-          float f[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint32_t w4[4];
@@ -260,21 +259,9 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
               }
               __nv_bfloat162 hp = __floats2bfloat162_rn(a, b);
               w4[i] = *reinterpret_cast<uint32_t*>(&hp);
-              f[j + 2 * i] = __uint_as_float(w4[i] << 16);
-              f[j + 2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u);
             }
             const uint32_t chunk = (uint32_t)((part + j) >> 3);  // 16-byte chunk within the staged row
             st_shared_v4(row_addr + ((chunk ^ swz) << 4), w4[0], w4[1], w4[2], w4[3]);
-          }
-          if (p.stats) {
-            float sq[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
-            warp_transpose_sum(f, lane);
-            warp_transpose_sum(sq, lane);
-            const uint32_t sa = stats_sm + 4 * (co0 + col + lane);
-            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa), "f"(f[0]) : "memory");
-            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa + 4 * p.k_total), "f"(sq[0]) : "memory");
           }
         }
         fence_proxy_async();
@@ -282,10 +269,58 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         if (issuer) {
           const int cc = co0 + sb * p.store_c;
           if (p.convt)
-            tma_store_5d(&p.map_out, sbuf, cc, tap2 & 1, twi * p.tw, tap2 >> 1, img * p.h + thi * p.th);
+            tma_store_4d(&p.map_out, sbuf, cc, twi * p.tw, kh, img * p.h + thi * p.th);
           else
             tma_store_2d(&p.map_out, sbuf, cc, ((img * p.h + thi * p.th) * p.w + twi * p.tw));
           bulk_commit();
+        }
+        if (p.stats) {
+          // column sums of the staged (rounded) tile: 128 threads = column pairs x row groups, conflict-free LDS.32
+          const int t = q * 32 + lane;
+          int cp, r0;
+          if (p.store_c == 64) {
+            cp = t & 31;
+            r0 = t >> 5;        // rows r0, r0 + 4, ...
+          } else {
+            cp = t & 15;
+            const int rg = t >> 4;
+            r0 = rg;            // rows r0, r0 + 8, ...: lanes 0-15 / 16-31 read adjacent rows (different banks)
+          }
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          // rows r0 + 8 i (+ 4 for 128-byte rows): the swizzle term repeats every 8 rows, so the addresses are base + i * stride
+          const uint32_t inrow = ((uint32_t)(cp & 3) << 2);
+          const uint32_t sw0 = p.store_c == 64 ? (uint32_t)(r0 & 7) : (uint32_t)((r0 >> 1) & 3);
+          const uint32_t a0 = sbuf + r0 * rowb + ((((uint32_t)cp >> 2) ^ sw0) << 4) + inrow;
+          const uint32_t a1 = sbuf + (r0 + 4) * rowb + ((((uint32_t)cp >> 2) ^ (uint32_t)((r0 + 4) & 7)) << 4) + inrow;
+          const uint32_t stride = 8 * rowb;
+          uint32_t wv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[i]) : "r"(a0 + i * stride));
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a = __uint_as_float(wv[i] << 16), b = __uint_as_float(wv[i] & 0xffff0000u);
+            s0 += a;
+            s1 += b;
+            q0 = fmaf(a, a, q0);
+            q1 = fmaf(b, b, q1);
+          }
+          if (p.store_c == 64) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[i]) : "r"(a1 + i * stride));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = __uint_as_float(wv[i] << 16), b = __uint_as_float(wv[i] & 0xffff0000u);
+              s0 += a;
+              s1 += b;
+              q0 = fmaf(a, a, q0);
+              q1 = fmaf(b, b, q1);
+            }
+          }
+          const uint32_t sa = stats_sm + 4 * (co0 + sb * p.store_c + 2 * cp);
+          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa), "f"(s0) : "memory");
+          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa + 4), "f"(s1) : "memory");
+          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa + 4 * p.k_total), "f"(q0) : "memory");
+          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa + 4 * p.k_total + 4), "f"(q1) : "memory");
         }
       }
       tc_fence_before();
@@ -650,14 +685,17 @@ static int encode_out_map(CUtensorMap* m, void* ptr, long long pixels, int k, in
   }
   return XV2_OK;
 }
-// transposed conv: output (n, 2h, 2w, k) viewed as {k, 2 (kw), w, 2 (kh), h*n}
-static int encode_out_shuffle_map(CUtensorMap* m, void* ptr, int n, int h, int w, int k, int ldo, int box_c, int tw, int th) {
-  cuuint64_t dims[5] = {(cuuint64_t)k, 2, (cuuint64_t)w, 2, (cuuint64_t)h * n};
-  cuuint64_t strides[4] = {(cuuint64_t)ldo * 2, (cuuint64_t)2 * ldo * 2, (cuuint64_t)2 * w * ldo * 2,
-                           (cuuint64_t)4 * w * ldo * 2};
-  cuuint32_t box[5] = {(cuuint32_t)box_c, 1, (cuuint32_t)tw, 1, (cuuint32_t)th};
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+int strip_encode_out(CUtensorMap* m, void* ptr, long long pixels, int k, int ldo, int box_c) {
+  return encode_out_map(m, ptr, pixels, k, ldo, box_c);
+}
+// transposed conv: the (kw, k) pair of an input pixel is CONTIGUOUS in the (n, 2h, 2w, k) output (pixels 2w, 2w+1 of one row),
+// so the output is viewed as {2k (kw-major), w, 2 (kh), h*n} and a staged block is a full 64/128-byte row segment
+static int encode_out_shuffle_map(CUtensorMap* m, void* ptr, int n, int h, int w, int k, int box_c, int tw, int th) {
+  cuuint64_t dims[4] = {(cuuint64_t)2 * k, (cuuint64_t)w, 2, (cuuint64_t)h * n};
+  cuuint64_t strides[3] = {(cuuint64_t)2 * k * 2, (cuuint64_t)2 * w * k * 2, (cuuint64_t)4 * w * k * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)tw, 1, (cuuint32_t)th};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -757,7 +795,7 @@ extern "C" int xv2_conv_tc(const xv2_tc_conv* q, const void* src0, const void* s
   p.cg = cg;
   p.kg = kg;
   p.bn = bn;
-  const bool tma_store = q->out_dtype == XV2_BF16 && bn % 32 == 0;
+  const bool tma_store = q->out_dtype == XV2_BF16 && bn % 32 == 0 && !(convt && (ldo != q->k || bias));
   if (stats && (!tma_store || convt || q->k > 2048)) {
     set_error("conv_tc: fused statistics epilogue is not available for this shape");
     return XV2_EUNSUPPORTED;
@@ -766,7 +804,7 @@ extern "C" int xv2_conv_tc(const xv2_tc_conv* q, const void* src0, const void* s
   if (tma_store) {
     p.tma_store = 1;
     p.store_c = (bn % 64 == 0 && bn > 64) ? 64 : 32;
-    rc = convt ? encode_out_shuffle_map(&p.map_out, out, q->n, q->h, q->w, q->k, ldo, p.store_c, tw, th)
+    rc = convt ? encode_out_shuffle_map(&p.map_out, out, q->n, q->h, q->w, q->k, p.store_c, tw, th)
                : encode_out_map(&p.map_out, out, (long long)q->n * q->h * q->w, q->k, ldo, p.store_c);
     if (rc) return rc;
     extra = 1024 + 2 * 16384 + (stats ? 8u * q->k : 0u);

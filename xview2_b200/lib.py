@@ -35,14 +35,20 @@ _SIGNATURES = {
     "xv2_init": [I32],
     "xv2_conv_gather_simt": [POINTER(ConvGeom), P, P, P, P, P],
     "xv2_conv_wgrad_simt": [POINTER(ConvGeom), P, P, P, P],
+    "xv2_stem_conv_fwd": [P, P, P, I32, I32, I32, I32, P],
+    "xv2_stem_conv_wgrad": [P, P, P, I32, I32, I32, I32, P],
+    "xv2_fc_fwd": [P, P, P, P, I32, I32, I32, P],
+    "xv2_fc_wgrad": [P, P, P, P, I32, I32, I32, P],
     "xv2_colsum": [P, I64, I32, I32, P, P],
     "xv2_pack_weight": [P, P, I32, I32, I32, I32, I32, I32, I32, P],
+    "xv2_pack_weights_batched": [P, I32, P],
     "xv2_conv_tc": [POINTER(TcConv), P, P, P, P, P, P, P],
     "xv2_wgrad_tc": [POINTER(TcConv), P, P, P, I32, P, P],
     "xv2_bn_stats": [P, I64, I32, I32, P, P],
     "xv2_bn_finalize": [P, I64, I32, P, P, P, P, F, F, P, P, P, P, P],
     "xv2_bn_eval_coeffs": [I32, P, P, P, P, F, P, P, P],
     "xv2_bn_apply": [P, P, P, I64, I32, I32, P, P, I32, P],
+    "xv2_bn_train_apply": [P, P, P, I64, I32, I32, P, I64, P, P, P, P, F, F, P, I32, P],
     "xv2_bn_bwd_reduce": [P, P, P, I64, I32, I32, P, P, P, P, I32, P, P],
     "xv2_bn_bwd_apply": [P, P, P, P, P, I64, I32, I32, P, P, P, P, P, I32, P, I64, P, P, P],
     "xv2_maxpool_fwd": [P, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],

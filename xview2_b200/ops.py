@@ -69,6 +69,8 @@ def pack_weight(weight, mode, dtype, groups=1):
         torch.empty(w.numel(), dtype=dtype, device=w.device)
     call("xv2_pack_weight", ptr(w), ptr(out), a, r, s, b, groups, mode, dtype_code(out))
     cache[(mode, dtype, groups)] = (stamp, out)
+    import weakref
+    _pack_registry[(id(weight), mode, dtype, groups)] = (weakref.ref(weight), out)
     return out
 
 
@@ -76,6 +78,44 @@ def clear_weight_cache():
     """Invalidates every packed weight copy (called after kernels rewrite the master weights in place)."""
     global _pack_epoch
     _pack_epoch += 1
+
+
+_pack_registry = {}   # (id(weight), mode, dtype, groups) -> (weakref to weight, packed tensor)
+_pack_table = None    # (registry size, device job table, keep-alive list)
+
+
+def repack_all():
+    """Refreshes EVERY packed copy known so far with one launch (xv2_pack_weights_batched) and stamps them valid for the
+    current parameter values.  Called by the fused optimizers right after they rewrote the flat master buffer, so the
+    per-layer lazy re-pack (171 launches per step at ResNeSt-50) disappears from the step."""
+    global _pack_table
+    import numpy as np
+
+    live = []
+    for key, (ref, out) in list(_pack_registry.items()):
+        w = ref()
+        if w is None or not w.is_cuda or w.__dict__.get("_xv2_pack", {}).get(key[1:], (None, None))[1] is not out:
+            del _pack_registry[key]
+            continue
+        live.append((key, w, out))
+    if not live:
+        return
+    sig = tuple((k, w.data_ptr(), o.data_ptr()) for k, w, o in live)
+    if _pack_table is None or _pack_table[0] != sig:
+        rows = np.zeros((len(live), 6), dtype=np.int64)  # sizeof(xv2_pack_job) = 8 + 8 + 8 * 4 = 48 bytes
+        for i, (key, w, out) in enumerate(live):
+            _, mode, dtype, groups = key
+            phys = _weight_phys(w)
+            a, b, r, s = phys.shape
+            rows[i, 0] = phys.data_ptr()
+            rows[i, 1] = out.data_ptr()
+            ints = np.array([a, r, s, b, groups, mode, dtype_code(out), 0], dtype=np.int32)
+            rows[i, 2:6] = ints.view(np.int64)
+        table = torch.from_numpy(rows).to(live[0][1].device)
+        _pack_table = (sig, table)
+    call("xv2_pack_weights_batched", ptr(_pack_table[1]), len(live))
+    for key, w, out in live:
+        w.__dict__["_xv2_pack"][key[1:]] = ((w._version, _pack_epoch, w.data_ptr()), out)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -125,6 +165,13 @@ class _Conv2d(torch.autograd.Function):
         ctx.cfg = (stride, pad, dil, groups, c0, c1)
         ctx.save_for_backward(x, x2, weight)
         ctx.has_bias = bias is not None
+        ctx.stem = (_tc_ok(x) and stride == 2 and r == 3 and s == 3 and pad == 1 and dil == 1 and c0 == 3 and c1 == 0 and
+                    groups == 1 and k in (32, 64) and bias is None)
+        if ctx.stem:  # Cin = 3 stride-2 stem conv: direct CUDA-core kernel (K = 27 is no tensor-core shape)
+            out = empty_act(n, k, oh, ow, x.dtype, x.device)
+            lib.note_work(2.0 * n * oh * ow * k * 27, 2.0 * n * (h * w * 3 + oh * ow * k), f"stem n{n} {h}x{w} k{k}")
+            call("xv2_stem_conv_fwd", ptr(x), ptr(_weight_phys(weight)), ptr(out), n, h, w, k)
+            return out, None
         use_tc = _tc_ok(x) and stride == 1 and oh == h and ow == w
         if use_tc:
             wp = pack_weight(weight, 0, torch.bfloat16, groups)
@@ -202,6 +249,10 @@ class _Conv2d(torch.autograd.Function):
                               f"wgrad n{n} {h}x{w} c{c0}+{c1} k{k} {r}x{s} g{groups}")
                 rc = call("xv2_wgrad_tc", p, ptr(x), ptr(x2), ptr(dy), 0, ptr(dw), allow_unsupported=True)
                 done = rc == 0
+            if not done and ctx.stem:
+                lib.note_work(2.0 * n * oh * ow * k * 27, 2.0 * n * (h * w * 3 + oh * ow * k), f"stem wgrad n{n} {h}x{w} k{k}")
+                call("xv2_stem_conv_wgrad", ptr(x), ptr(dy), ptr(dw), n, h, w, k)
+                done = True
             if not done:
                 src = x if x2 is None else nhwc(torch.cat((x, x2), 1))
                 g = ConvGeom(n, h, w, c0 + c1, oh, ow, k, r, s, stride, pad, dil, 1, groups, dtype_code(x), F32)
@@ -320,15 +371,16 @@ class _BatchNormAct(torch.autograd.Function):
             if stats is None:
                 stats = torch.zeros(2 * c, dtype=torch.float64, device=dev)
                 call("xv2_bn_stats", ptr(x), pixels, c, dtype_code(x), ptr(stats))
-            call("xv2_bn_finalize", ptr(stats), pixels, c, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
-                 float(momentum), float(eps), ptr(mean), ptr(invstd), ptr(scale), ptr(shift))
+            y = torch.empty_like(x)
+            call("xv2_bn_train_apply", ptr(x), ptr(residual), ptr(y), pixels, c, dtype_code(x), ptr(stats), pixels, ptr(gamma),
+                 ptr(beta), ptr(running_mean), ptr(running_var), float(momentum), float(eps), ptr(coef), act)
         else:
             mean.copy_(running_mean)
             invstd.copy_(torch.rsqrt(running_var + eps))
             call("xv2_bn_eval_coeffs", c, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), float(eps),
                  ptr(scale), ptr(shift))
-        y = torch.empty_like(x)
-        call("xv2_bn_apply", ptr(x), ptr(residual), ptr(y), pixels, c, dtype_code(x), ptr(scale), ptr(shift), act)
+            y = torch.empty_like(x)
+            call("xv2_bn_apply", ptr(x), ptr(residual), ptr(y), pixels, c, dtype_code(x), ptr(scale), ptr(shift), act)
         ctx.save_for_backward(x, residual, gamma, coef)
         ctx.cfg = (training, act)
         return y
@@ -452,6 +504,9 @@ def _fc(x2d, w2d, bias):
     n, c = x2d.shape
     k = w2d.shape[0]
     out = torch.empty((n, k), dtype=torch.float32, device=x2d.device)
+    if c % 4 == 0:
+        call("xv2_fc_fwd", ptr(x2d), ptr(w2d), ptr(bias), ptr(out), n, c, k)
+        return out
     g = ConvGeom(n, 1, 1, c, 1, 1, k, 1, 1, 1, 0, 1, 1, 1, F32, F32)
     call("xv2_conv_gather_simt", g, ptr(x2d), ptr(w2d), ptr(bias), ptr(out))
     return out
@@ -460,6 +515,11 @@ def _fc(x2d, w2d, bias):
 def _fc_wgrad(x2d, dy2d):
     n, c = x2d.shape
     k = dy2d.shape[1]
+    if c % 4 == 0:
+        dw = torch.empty((k, c), dtype=torch.float32, device=x2d.device)
+        db = torch.empty(k, dtype=torch.float32, device=x2d.device)
+        call("xv2_fc_wgrad", ptr(x2d), ptr(dy2d), ptr(dw), ptr(db), n, c, k)
+        return dw, db
     dw = torch.zeros((k, c), dtype=torch.float32, device=x2d.device)
     g = ConvGeom(n, 1, 1, c, 1, 1, k, 1, 1, 1, 0, 1, 1, 1, F32, F32)
     call("xv2_conv_wgrad_simt", g, ptr(x2d), ptr(dy2d), ptr(dw))

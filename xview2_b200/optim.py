@@ -118,7 +118,8 @@ class FusedAdamW(_FlatOptimizer):
         self.step_count += 1
         ops.adamw_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1],
                        g["eps"], g["weight_decay"], self.step_count, self.grad_scale)
-        ops.clear_weight_cache()  # packed bf16 weight copies are stale now
+        ops.clear_weight_cache()  # packed bf16 weight copies are stale now ...
+        ops.repack_all()          # ... and refreshed by one batched launch
 
 
 class FusedSGD(_FlatOptimizer):
@@ -137,3 +138,4 @@ class FusedSGD(_FlatOptimizer):
         ops.sgd_step(self.flat.data, self.flat.grad, self.momentum_buffer, g["lr"], g["momentum"], self.grad_scale,
                      self.step_count)
         ops.clear_weight_cache()
+        ops.repack_all()
