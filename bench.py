@@ -178,7 +178,8 @@ def run_ours(a):
         raise RuntimeError("bench.py measures the CUDA path; no GPU is visible (there is no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     lib.init(local)
     dev = torch.device("cuda", local)
     B, S = a.batch, a.size
@@ -259,10 +260,13 @@ def run_ours(a):
     e2e_value = B * world * a.steps / (float(ms2) / 1e3)
 
     # ---- roofline of the dominant kernel: instrumented step (CUDA events around every libxv2 launch) -------------
+    # EVERY rank runs the step (it contains the gradient all-reduce); only rank 0 records the events
     roof = kernels = None
     if rank == 0:
         lib.profile_start()
-        train_step(resident)
+    train_step(resident)
+    fence()
+    if rank == 0:
         prof = lib.profile_stop()
         total = sum(d["ms"] for d in prof.values()) or 1.0
         kernels = {k: {"calls": d["calls"], "ms": round(d["ms"], 3), "share": round(d["ms"] / total, 4),

@@ -184,6 +184,20 @@ int xv2_splat_gap(const void* x, float* gap, int32_t n, int64_t hw, int32_t c, i
 /* att[n][2c] (fp32) = softmax over the radix pair of logits[n][2c] */
 int xv2_rsoftmax_fwd(const float* logits, float* att, int32_t n, int32_t c, void* stream);
 int xv2_rsoftmax_bwd(const float* att, const float* datt, float* dlogits, int32_t n, int32_t c, void* stream);
+/* The FC chain between GAP and the attention weights, fused (n <= 32 samples):
+ *   forward : z1 = fc1(gap) [n][inter] -> BatchNorm over the n samples (training != 0: batch statistics, running statistics
+ *             updated; else running statistics) -> relu = a1 -> fc2 -> r-softmax = att [n][2c].
+ *             coef = [4][inter] mean | invstd | scale | shift (saved for backward).  Replaces fc1 / bn1 / relu / fc2 / rSoftMax.
+ *   backward: from datt [n][2c]; w2t = fc2 weight transposed [inter][2c], w1t = fc1 weight transposed [c][inter];
+ *             writes dw2 [2c][inter], db2, dw1 [inter][c], db1, dgamma, dbeta, dgap [n][c]; dz2 / dz1 are scratch. */
+int xv2_splat_fc_fwd(const float* gap, const float* w1, const float* b1, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps, int32_t training, const float* w2,
+                     const float* b2, float* z1, float* a1, float* coef, float* att, int32_t n, int32_t c, int32_t inter,
+                     void* stream);
+int xv2_splat_fc_bwd(const float* att, const float* datt, const float* a1, const float* z1, const float* coef,
+                     const float* gamma, const float* gap, const float* w2t, const float* w1t, int32_t training, float* dz2,
+                     float* dz1, float* dw2, float* db2, float* dw1, float* db1, float* dgamma, float* dbeta, float* dgap,
+                     int32_t n, int32_t c, int32_t inter, void* stream);
 /* out[n][hw][c] = att[n][c]*x[..,c] + att[n][C+c]*x[..,C+c] */
 int xv2_splat_combine(const void* x, const float* att, void* out, int32_t n, int64_t hw, int32_t c, int32_t dtype,
                       void* stream);

@@ -238,3 +238,237 @@ extern "C" int xv2_fc_wgrad(const float* x, const float* dy, float* dw, float* d
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }
+
+// ====================================================================================================================
+// Split-attention FC chain (SplAtConv2d tail on [n][C] vectors, n <= 32), fused to 2 forward + 3 backward launches:
+//   forward  A: z1 = fc1(gap) -> BatchNorm over the n samples (train: batch statistics + running update) -> relu -> a1
+//            B: z2 = fc2(a1) -> r-softmax over the radix pair (k, k + C) -> att
+//   backward 1: dz2 = rsoftmax'(att, datt); dw2 = dz2^T a1; db2
+//            2: da1 = dz2 w2 -> relu' -> BatchNorm backward over n -> dz1; dw1 = dz1^T gap; db1, dgamma, dbeta
+//            3: dgap = dz1 w1
+// One warp per output channel; lanes stride over the reduction axis with float4 loads; all n rows per pass.
+// ====================================================================================================================
+namespace xv2 {
+constexpr int kSaMaxN = 32;
+
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+}
+// out[i] (all lanes) = sum_c x[i][c] * w[c] for i < n; c % 4 == 0
+__device__ __forceinline__ void warp_matvec(const float* __restrict__ x, const float* __restrict__ w, int n, int c, int lane,
+                                            float* out) {
+  const int c4 = c >> 2;
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  for (int n0 = 0; n0 < n; n0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int j = lane; j < c4; j += 32) {
+      const float4 wv = __ldg(wr + j);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (n0 + i < n) acc[i] = dot4(wv, __ldg(reinterpret_cast<const float4*>(x + (long long)(n0 + i) * c) + j), acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (n0 + i < n) out[n0 + i] = warp_sum(acc[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) sa_fc1_bn_relu_kernel(const float* __restrict__ gap, const float* __restrict__ w1,
+                                                             const float* __restrict__ b1, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ rmean,
+                                                             float* __restrict__ rvar, float momentum, float eps, int training,
+                                                             float* __restrict__ z1, float* __restrict__ a1,
+                                                             float* __restrict__ coef, int n, int c, int inter) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= inter) return;
+  float z[kSaMaxN];
+  warp_matvec(gap, w1 + (long long)j * c, n, c, lane, z);
+  const float bj = b1 ? b1[j] : 0.f;
+  float mean, var;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < n; ++i) {
+      z[i] += bj;
+      s += z[i];
+      q += (double)z[i] * z[i];
+    }
+    const double mu = s / n;
+    double v = q / n - mu * mu;
+    if (v < 0.0) v = 0.0;
+    mean = (float)mu;
+    var = (float)v;
+    if (lane == 0 && rmean) {
+      const double unbiased = n > 1 ? v * n / (n - 1.0) : v;
+      rmean[j] = (1.f - momentum) * rmean[j] + momentum * mean;
+      rvar[j] = (1.f - momentum) * rvar[j] + momentum * (float)unbiased;
+    }
+  } else {
+    for (int i = 0; i < n; ++i) z[i] += bj;
+    mean = rmean[j];
+    var = rvar[j];
+  }
+  const float is = training ? (float)(1.0 / sqrt((double)var + (double)eps)) : 1.0f / sqrtf(var + eps);
+  const float g = gamma ? gamma[j] : 1.f, b = beta ? beta[j] : 0.f;
+  const float sc = g * is, sh = b - mean * g * is;
+  if (lane == 0) {
+    coef[j] = mean;
+    coef[inter + j] = is;
+    coef[2 * inter + j] = sc;
+    coef[3 * inter + j] = sh;
+  }
+  for (int i = lane; i < n; i += 32) {
+    z1[(long long)i * inter + j] = z[i];
+    const float u = fmaf(z[i], sc, sh);
+    a1[(long long)i * inter + j] = u > 0.f ? u : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) sa_fc2_rsoftmax_kernel(const float* __restrict__ a1, const float* __restrict__ w2,
+                                                              const float* __restrict__ b2, float* __restrict__ att, int n,
+                                                              int c, int inter) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= c) return;
+  float z0[kSaMaxN], z1[kSaMaxN];
+  warp_matvec(a1, w2 + (long long)k * inter, n, inter, lane, z0);
+  warp_matvec(a1, w2 + (long long)(k + c) * inter, n, inter, lane, z1);
+  const float b0 = b2 ? b2[k] : 0.f, bb1 = b2 ? b2[k + c] : 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const float a = z0[i] + b0, b = z1[i] + bb1;
+    const float m = fmaxf(a, b);
+    const float ea = expf(a - m), eb = expf(b - m);
+    const float inv = 1.f / (ea + eb);
+    att[(long long)i * 2 * c + k] = ea * inv;
+    att[(long long)i * 2 * c + c + k] = eb * inv;
+  }
+}
+
+// backward 1: warp per radix pair k: dz2[:, k], dz2[:, k + C]; dw2 rows; db2
+__global__ void __launch_bounds__(256) sa_bwd_fc2_kernel(const float* __restrict__ att, const float* __restrict__ datt,
+                                                         const float* __restrict__ a1, float* __restrict__ dz2,
+                                                         float* __restrict__ dw2, float* __restrict__ db2, int n, int c,
+                                                         int inter) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= c) return;
+  float d0[kSaMaxN], d1[kSaMaxN];
+  float s0 = 0.f, s1 = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const long long i0 = (long long)i * 2 * c + k, i1 = i0 + c;
+    const float p0 = att[i0], p1 = att[i1], g0 = datt[i0], g1 = datt[i1];
+    const float dot = p0 * g0 + p1 * g1;
+    d0[i] = p0 * (g0 - dot);
+    d1[i] = p1 * (g1 - dot);
+    s0 += d0[i];
+    s1 += d1[i];
+  }
+  if (lane == 0) {
+    db2[k] = s0;
+    db2[k + c] = s1;
+  }
+  for (int i = lane; i < n; i += 32) {
+    dz2[(long long)i * 2 * c + k] = d0[i];
+    dz2[(long long)i * 2 * c + c + k] = d1[i];
+  }
+  for (int j = lane; j < inter; j += 32) {
+    float w0 = 0.f, w1 = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const float a = a1[(long long)i * inter + j];
+      w0 = fmaf(d0[i], a, w0);
+      w1 = fmaf(d1[i], a, w1);
+    }
+    dw2[(long long)k * inter + j] = w0;
+    dw2[(long long)(k + c) * inter + j] = w1;
+  }
+}
+
+// backward 2: warp per fc1 output channel j.  w2t is fc2's weight transposed: [inter][2c]
+__global__ void __launch_bounds__(256) sa_bwd_bn_fc1_kernel(const float* __restrict__ dz2, const float* __restrict__ w2t,
+                                                            const float* __restrict__ z1, const float* __restrict__ coef,
+                                                            const float* __restrict__ gamma, const float* __restrict__ gap,
+                                                            int training, float* __restrict__ dz1, float* __restrict__ dw1,
+                                                            float* __restrict__ db1, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int n, int c, int inter) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= inter) return;
+  float da[kSaMaxN];
+  warp_matvec(dz2, w2t + (long long)j * 2 * c, n, 2 * c, lane, da);
+  const float mean = coef[j], is = coef[inter + j], sc = coef[2 * inter + j], sh = coef[3 * inter + j];
+  const float g = gamma ? gamma[j] : 1.f;
+  float r1 = 0.f, r2 = 0.f;
+  float xh[kSaMaxN];
+  for (int i = 0; i < n; ++i) {
+    const float z = z1[(long long)i * inter + j];
+    const float u = fmaf(z, sc, sh);
+    da[i] = u > 0.f ? da[i] : 0.f;  // relu'
+    xh[i] = (z - mean) * is;
+    r1 += da[i];
+    r2 = fmaf(da[i], xh[i], r2);
+  }
+  float d[kSaMaxN];
+  float bsum = 0.f;
+  const float inv_n = 1.f / (float)n;
+  for (int i = 0; i < n; ++i) {
+    d[i] = training ? g * is * (da[i] - r1 * inv_n - xh[i] * r2 * inv_n) : da[i] * sc;
+    bsum += d[i];
+  }
+  if (lane == 0) {
+    dbeta[j] = r1;
+    dgamma[j] = r2;
+    db1[j] = bsum;
+  }
+  for (int i = lane; i < n; i += 32) dz1[(long long)i * inter + j] = d[i];
+  for (int cc = lane; cc < c; cc += 32) {
+    float w = 0.f;
+    for (int i = 0; i < n; ++i) w = fmaf(d[i], gap[(long long)i * c + cc], w);
+    dw1[(long long)j * c + cc] = w;
+  }
+}
+
+// backward 3: dgap[n][c] = sum_j dz1[n][j] w1t[c][j]  (w1t = fc1's weight transposed: [c][inter]); warp per channel c
+__global__ void __launch_bounds__(256) sa_bwd_gap_kernel(const float* __restrict__ dz1, const float* __restrict__ w1t,
+                                                         float* __restrict__ dgap, int n, int c, int inter) {
+  const int lane = threadIdx.x & 31;
+  const int cc = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (cc >= c) return;
+  float o[kSaMaxN];
+  warp_matvec(dz1, w1t + (long long)cc * inter, n, inter, lane, o);
+  for (int i = lane; i < n; i += 32) dgap[(long long)i * c + cc] = o[i];
+}
+}  // namespace xv2
+
+extern "C" int xv2_splat_fc_fwd(const float* gap, const float* w1, const float* b1, const float* gamma, const float* beta,
+                                float* running_mean, float* running_var, float momentum, float eps, int32_t training,
+                                const float* w2, const float* b2, float* z1, float* a1, float* coef, float* att, int32_t n,
+                                int32_t c, int32_t inter, void* stream) {
+  XV2_REQUIRE(gap && w1 && w2 && z1 && a1 && coef && att, "splat_fc_fwd: null argument");
+  XV2_REQUIRE(n >= 1 && n <= kSaMaxN && c % 4 == 0 && inter % 4 == 0, "splat_fc_fwd: n <= 32, channels multiples of 4 (n %d c %d inter %d)",
+              n, c, inter);
+  XV2_REQUIRE(training == 0 || n > 1, "Expected more than 1 value per channel when training");
+  XV2_REQUIRE(training != 0 || (running_mean && running_var), "splat_fc_fwd: eval mode needs running statistics");
+  sa_fc1_bn_relu_kernel<<<(inter + 7) / 8, 256, 0, as_stream(stream)>>>(gap, w1, b1, gamma, beta, running_mean, running_var, momentum,
+                                                                        eps, training, z1, a1, coef, n, c, inter);
+  sa_fc2_rsoftmax_kernel<<<(c + 7) / 8, 256, 0, as_stream(stream)>>>(a1, w2, b2, att, n, c, inter);
+  XV2_LAUNCH_CHECK();
+  return XV2_OK;
+}
+
+extern "C" int xv2_splat_fc_bwd(const float* att, const float* datt, const float* a1, const float* z1, const float* coef,
+                                const float* gamma, const float* gap, const float* w2t, const float* w1t, int32_t training,
+                                float* dz2, float* dz1, float* dw2, float* db2, float* dw1, float* db1, float* dgamma,
+                                float* dbeta, float* dgap, int32_t n, int32_t c, int32_t inter, void* stream) {
+  XV2_REQUIRE(att && datt && a1 && z1 && coef && gap && w2t && w1t && dz2 && dz1 && dw2 && db2 && dw1 && db1 && dgamma && dbeta &&
+                  dgap,
+              "splat_fc_bwd: null argument");
+  XV2_REQUIRE(n >= 1 && n <= kSaMaxN && c % 4 == 0 && inter % 4 == 0, "splat_fc_bwd: n <= 32, channels multiples of 4");
+  sa_bwd_fc2_kernel<<<(c + 7) / 8, 256, 0, as_stream(stream)>>>(att, datt, a1, dz2, dw2, db2, n, c, inter);
+  sa_bwd_bn_fc1_kernel<<<(inter + 7) / 8, 256, 0, as_stream(stream)>>>(dz2, w2t, z1, coef, gamma, gap, training, dz1, dw1, db1, dgamma,
+                                                                       dbeta, n, c, inter);
+  sa_bwd_gap_kernel<<<(c + 7) / 8, 256, 0, as_stream(stream)>>>(dz1, w1t, dgap, n, c, inter);
+  XV2_LAUNCH_CHECK();
+  return XV2_OK;
+}

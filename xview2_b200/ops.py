@@ -121,6 +121,17 @@ def repack_all():
 # ---------------------------------------------------------------------------------------------------------------
 # convolution
 # ---------------------------------------------------------------------------------------------------------------
+def _grad_buffer(weight):
+    """Where a weight-gradient kernel may ACCUMULATE directly: the parameter's own .grad when it is the zero-initialised fp32
+    view FlatParams installed (physical [K][R][S][C], same order the kernels write).  Returns (buffer, direct): with
+    direct=True the autograd function returns None for this weight, so autograd launches no zeros / add kernels for it."""
+    g = weight.grad
+    if (g is not None and g.dtype == torch.float32 and g.is_cuda and g.shape == weight.shape and
+            g.is_contiguous(memory_format=CL) and getattr(weight, "_xv2_flat", False)):
+        return g, True
+    return torch.zeros(weight.shape, dtype=torch.float32, device=weight.device).contiguous(memory_format=CL), False
+
+
 def _out_size(i, k, stride, pad, dil):
     return (i + 2 * pad - dil * (k - 1) - 1) // stride + 1
 
@@ -240,8 +251,9 @@ class _Conv2d(torch.autograd.Function):
                     dx = full
                 else:
                     dx, dx2 = nhwc(full[:, :c0]), nhwc(full[:, c0:])
+        direct = False
         if ctx.needs_input_grad[2]:
-            dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device).contiguous(memory_format=CL)
+            dw, direct = _grad_buffer(weight)
             done = False
             if tc:
                 p = TcConv(n, h, w, c0, c1, 0, 0, k, r, s, pad, dil, groups, 0, BF16, 0)
@@ -260,7 +272,7 @@ class _Conv2d(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = torch.zeros(k, dtype=torch.float32, device=x.device)
             _colsum(dy, db)
-        return dx, dx2, dw, db, None, None, None, None, None
+        return dx, dx2, (None if direct else dw), db, None, None, None, None, None
 
 
 def _colsum(t, out):
@@ -328,8 +340,9 @@ class _ConvT2x2(torch.autograd.Function):
             if not done:
                 wp = pack_weight(weight, 0, x.dtype)
                 dx = _conv_gather(dy, wp, None, n, 2 * h, 2 * w, cout, h, w, cin, 2, 2, 2, 0, 1, 1, 1, x.dtype)
+        direct = False
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device).contiguous(memory_format=CL)
+            dw, direct = _grad_buffer(weight)
             done = False
             if tc:
                 p = TcConv(n, h, w, cin, 0, 0, 0, cout, 2, 2, 0, 1, 1, 1, BF16, 0)
@@ -341,7 +354,7 @@ class _ConvT2x2(torch.autograd.Function):
                 # gradient of the stride-2 conv whose "input" is dy and "output" is x: dw[cin][kh][kw][cout]
                 g = ConvGeom(n, 2 * h, 2 * w, cout, h, w, cin, 2, 2, 2, 0, 1, 1, 1, dtype_code(x), F32)
                 call("xv2_conv_wgrad_simt", g, ptr(dy), ptr(x), ptr(dw))
-        return dx, dw
+        return dx, (None if direct else dw)
 
 
 def conv_transpose2x2(x, weight):
@@ -537,8 +550,8 @@ class _SplitAttention(torch.autograd.Function):
     """Whole split-attention tail as one tape node so that d(x) is written in a single pass.
 
     forward : gap = mean_hw(x0 + x1); a = r-softmax(fc2(relu(bn1(fc1(gap))))); out = a0*x0 + a1*x1
-    backward: datt = <dout, x_r>_hw  ->  tiny FC/BN chain  ->  dgap;  dx_r = a_r*dout + dgap/hw
-    The FC/BN arithmetic is fp32 on [n][c]-sized tensors and reuses the SIMT conv and BN kernels.
+    backward: datt = <dout, x_r>_hw  ->  FC/BN chain  ->  dgap;  dx_r = a_r*dout + dgap/hw
+    The FC/BN chain on the [n][C] vectors is fused into 2 forward + 3 backward launches (xv2_splat_fc_fwd / _bwd).
     """
 
     @staticmethod
@@ -549,28 +562,19 @@ class _SplitAttention(torch.autograd.Function):
         c = c2 // 2
         inter = w1.shape[0]
         dev = x.device
+        if training and n <= 1:
+            raise ValueError("Expected more than 1 value per channel when training")
+        if n > 32:
+            raise lib.Xv2Error("split attention serves batches of at most 32 tiles per GPU")
         gap = torch.empty((n, c), dtype=torch.float32, device=dev)
         call("xv2_splat_gap", ptr(x), ptr(gap), n, h * w, c, dtype_code(x))
         w1m, w2m = w1.reshape(inter, c).contiguous(), w2.reshape(c2, inter).contiguous()
-        z1 = _fc(gap, w1m, b1)
-        coef = torch.empty(4, inter, dtype=torch.float32, device=dev)
-        if training:
-            if n <= 1:
-                raise ValueError("Expected more than 1 value per channel when training")
-            st = torch.zeros(2 * inter, dtype=torch.float64, device=dev)
-            call("xv2_bn_stats", ptr(z1), n, inter, F32, ptr(st))
-            call("xv2_bn_finalize", ptr(st), n, inter, ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), float(momentum),
-                 float(eps), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]))
-        else:
-            coef[0].copy_(rmean)
-            coef[1].copy_(torch.rsqrt(rvar + eps))
-            call("xv2_bn_eval_coeffs", inter, ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), float(eps), ptr(coef[2]),
-                 ptr(coef[3]))
+        z1 = torch.empty((n, inter), dtype=torch.float32, device=dev)
         a1 = torch.empty_like(z1)
-        call("xv2_bn_apply", ptr(z1), None, ptr(a1), n, inter, F32, ptr(coef[2]), ptr(coef[3]), ACT_RELU)
-        z2 = _fc(a1, w2m, b2)
-        att = torch.empty_like(z2)
-        call("xv2_rsoftmax_fwd", ptr(z2), ptr(att), n, c)
+        coef = torch.empty(4, inter, dtype=torch.float32, device=dev)
+        att = torch.empty((n, c2), dtype=torch.float32, device=dev)
+        call("xv2_splat_fc_fwd", ptr(gap), ptr(w1m), ptr(b1), ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), float(momentum),
+             float(eps), int(bool(training)), ptr(w2m), ptr(b2), ptr(z1), ptr(a1), ptr(coef), ptr(att), n, c, inter)
         out = empty_act(n, c, h, w, x.dtype, dev)
         call("xv2_splat_combine", ptr(x), ptr(att), ptr(out), n, h * w, c, dtype_code(x))
         ctx.save_for_backward(x, att, gap, z1, a1, coef, w1, w2, gamma)
@@ -588,28 +592,20 @@ class _SplitAttention(torch.autograd.Function):
         dev = x.device
         datt = torch.zeros((n, c2), dtype=torch.float32, device=dev)
         call("xv2_splat_bwd_att", ptr(x), ptr(dout), ptr(datt), n, h * w, c, dtype_code(x))
-        dz2 = torch.empty_like(datt)
-        call("xv2_rsoftmax_bwd", ptr(att), ptr(datt), ptr(dz2), n, c)
-        dw2, db2 = _fc_wgrad(a1, dz2)
-        w2t = pack_weight(w2, 1, torch.float32).view(inter, c2)
-        da1 = _fc(dz2, w2t, None)
-        red = torch.zeros(2 * inter, dtype=torch.float64, device=dev)
-        call("xv2_bn_bwd_reduce", ptr(da1), ptr(z1), None, n, inter, F32, ptr(coef[2]), ptr(coef[3]), ptr(coef[0]),
-             ptr(coef[1]), ACT_RELU, ptr(red))
-        dz1 = torch.empty_like(z1)
-        dgb = torch.empty(2, inter, dtype=torch.float32, device=dev)
-        call("xv2_bn_bwd_apply", ptr(da1), ptr(z1), None, ptr(dz1), None, n, inter, F32, ptr(coef[2]), ptr(coef[3]),
-             ptr(coef[0]), ptr(coef[1]), ptr(gamma), ACT_RELU, ptr(red) if training else None, n,
-             ptr(dgb[0]) if training else None, ptr(dgb[1]) if training else None)
-        if not training:
-            dgb[1].copy_(red[:inter])
-            dgb[0].copy_(red[inter:])
-        dw1, db1 = _fc_wgrad(gap, dz1)
-        w1t = pack_weight(w1, 1, torch.float32).view(c, inter)
-        dgap = _fc(dz1, w1t, None)
+        w2t = pack_weight(w2, 1, torch.float32)  # [inter][2c]
+        w1t = pack_weight(w1, 1, torch.float32)  # [c][inter]
+        scratch = torch.empty(n * (c2 + inter), dtype=torch.float32, device=dev)
+        dw2 = torch.empty((c2, inter), dtype=torch.float32, device=dev)
+        dw1 = torch.empty((inter, c), dtype=torch.float32, device=dev)
+        small = torch.empty(c2 + 3 * inter, dtype=torch.float32, device=dev)
+        db2, db1, dgamma, dbeta = small[:c2], small[c2:c2 + inter], small[c2 + inter:c2 + 2 * inter], small[c2 + 2 * inter:]
+        dgap = torch.empty((n, c), dtype=torch.float32, device=dev)
+        call("xv2_splat_fc_bwd", ptr(att), ptr(datt), ptr(a1), ptr(z1), ptr(coef), ptr(gamma), ptr(gap), ptr(w2t), ptr(w1t),
+             int(bool(training)), ptr(scratch), ptr(scratch[n * c2:]), ptr(dw2), ptr(db2), ptr(dw1), ptr(db1), ptr(dgamma),
+             ptr(dbeta), ptr(dgap), n, c, inter)
         dx = torch.empty_like(x)
         call("xv2_splat_bwd_x", ptr(dout), ptr(att), ptr(dgap), ptr(dx), n, h * w, c, dtype_code(x))
-        return (dx, dw1.reshape(w1.shape), db1, dgb[0], dgb[1], None, None, dw2.reshape(w2.shape), db2, None, None, None)
+        return (dx, dw1.reshape(w1.shape), db1, dgamma, dbeta, None, None, dw2.reshape(w2.shape), db2, None, None, None)
 
 
 def split_attention(x, fc1, bn1, fc2):

@@ -48,6 +48,7 @@ class FlatParams:
                 view.copy_(p.data)
             p.data = view
             p.grad = gview
+            p._xv2_flat = True  # kernels may accumulate weight gradients straight into p.grad (ops._grad_buffer)
             off += (n + 3) // 4 * 4
         self.numel = total
         ops.clear_weight_cache()
