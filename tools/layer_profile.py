@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 import torch
 
 import bench
-from xview2_b200 import lib
+from xview2_b200 import lib, ops
 from xview2_b200.model.plt import Model
 
 ap = argparse.ArgumentParser()
@@ -25,6 +25,7 @@ a = ap.parse_args()
 a.gpus = 1
 torch.cuda.set_device(0)
 lib.init(0)
+ops.enable_wgrad_side_stream(True)
 ns = bench.config_namespace(a)
 torch.manual_seed(1)
 model = Model(ns).cuda().train()

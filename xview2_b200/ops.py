@@ -132,6 +132,75 @@ def _grad_buffer(weight):
     return torch.zeros(weight.shape, dtype=torch.float32, device=weight.device).contiguous(memory_format=CL), False
 
 
+# Weight gradients are leaves of the backward pass (only the optimizer reads them), so they are issued on a SIDE stream and
+# overlap the batch-norm / data-gradient chain of the layers below (tensor-pipe work next to HBM-bound work).
+import os as _os
+
+# Opt-in (bench.py / Trainer.fit switch it on): whoever reads .grad must call sync_side_streams() first -- FlatParams'
+# all_reduce_grads(), zero_grad() and the fused optimizers' step() do.
+WGRAD_SIDE_STREAM = False
+
+
+def enable_wgrad_side_stream(on=True):
+    global WGRAD_SIDE_STREAM
+    # measured (r01, C2 step): no gain while the wgrad and BN kernels cannot co-reside on an SM (185 KB + 112 KB of shared
+    # memory) and record_stream() churns the allocator -> off unless XV2_WGRAD_STREAM=1
+    WGRAD_SIDE_STREAM = bool(on) and _os.environ.get("XV2_WGRAD_STREAM", "0") == "1"
+_side_streams = {}
+_side_dirty = set()
+
+
+def _side_stream(device):
+    st = _side_streams.get(device.index)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _side_streams[device.index] = st
+    return st
+
+
+class _OnSide:
+    """Context: kernels launched inside run on the side stream after everything already queued on the current stream;
+    the listed tensors are kept alive (allocator-wise) until the side stream has consumed them."""
+
+    def __init__(self, device, *tensors):
+        self.side = _side_stream(device)
+        self.tensors = [t for t in tensors if t is not None]
+        self.ctx = None
+
+    def __enter__(self):
+        self.side.wait_stream(torch.cuda.current_stream())
+        for t in self.tensors:
+            t.record_stream(self.side)
+        _side_dirty.add(self.side)
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self.ctx.__exit__(*exc)
+
+
+def sync_side_streams():
+    """The current stream waits for every weight gradient issued on a side stream (called before the gradient all-reduce /
+    optimizer step / anything that reads .grad)."""
+    cur = torch.cuda.current_stream() if torch.cuda.is_available() else None
+    for st in list(_side_dirty):
+        cur.wait_stream(st)
+    _side_dirty.clear()
+
+
+class _Inline:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _wgrad_scope(direct, device, *tensors):
+    return _OnSide(device, *tensors) if (direct and WGRAD_SIDE_STREAM and lib._profile is None) else _Inline()
+
+
 def _out_size(i, k, stride, pad, dil):
     return (i + 2 * pad - dil * (k - 1) - 1) // stride + 1
 
@@ -259,7 +328,8 @@ class _Conv2d(torch.autograd.Function):
                 p = TcConv(n, h, w, c0, c1, 0, 0, k, r, s, pad, dil, groups, 0, BF16, 0)
                 lib.note_work(2.0 * n * h * w * k * cg * r * s, 2.0 * n * h * w * (c0 + c1 + k) + 4.0 * k * cg * r * s,
                               f"wgrad n{n} {h}x{w} c{c0}+{c1} k{k} {r}x{s} g{groups}")
-                rc = call("xv2_wgrad_tc", p, ptr(x), ptr(x2), ptr(dy), 0, ptr(dw), allow_unsupported=True)
+                with _wgrad_scope(direct, x.device, x, x2, dy):
+                    rc = call("xv2_wgrad_tc", p, ptr(x), ptr(x2), ptr(dy), 0, ptr(dw), allow_unsupported=True)
                 done = rc == 0
             if not done and ctx.stem:
                 lib.note_work(2.0 * n * oh * ow * k * 27, 2.0 * n * (h * w * 3 + oh * ow * k), f"stem wgrad n{n} {h}x{w} k{k}")
@@ -348,7 +418,8 @@ class _ConvT2x2(torch.autograd.Function):
                 p = TcConv(n, h, w, cin, 0, 0, 0, cout, 2, 2, 0, 1, 1, 1, BF16, 0)
                 lib.note_work(8.0 * n * h * w * cin * cout, 2.0 * n * h * w * (cin + 4 * cout) + 16.0 * cin * cout,
                               f"convT wgrad n{n} {h}x{w} c{cin} k{cout}")
-                rc = call("xv2_wgrad_tc", p, ptr(x), None, ptr(dy), 0, ptr(dw), allow_unsupported=True)
+                with _wgrad_scope(direct, x.device, x, dy):
+                    rc = call("xv2_wgrad_tc", p, ptr(x), None, ptr(dy), 0, ptr(dw), allow_unsupported=True)
                 done = rc == 0
             if not done:
                 # gradient of the stride-2 conv whose "input" is dy and "output" is x: dw[cin][kh][kw][cout]

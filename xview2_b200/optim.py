@@ -54,11 +54,13 @@ class FlatParams:
         ops.clear_weight_cache()
 
     def zero_grad(self):
+        ops.sync_side_streams()
         self.grad.zero_()
 
     def all_reduce_grads(self, group=None):
         """all-reduce(SUM) of the flat gradient buffer over the data-parallel ranks; returns the world size (the 1/N
         average is applied by the optimizer through its ``grad_scale``)."""
+        ops.sync_side_streams()  # weight gradients issued on the side stream have landed in the flat buffer
         dist = torch.distributed
         if not (dist.is_available() and dist.is_initialized()):
             return 1
@@ -115,6 +117,7 @@ class FusedAdamW(_FlatOptimizer):
         return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
 
     def step(self):
+        ops.sync_side_streams()
         g = self.param_groups[0]
         self.step_count += 1
         ops.adamw_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1],
@@ -134,6 +137,7 @@ class FusedSGD(_FlatOptimizer):
         return {"momentum_buffer": self.momentum_buffer}
 
     def step(self):
+        ops.sync_side_streams()
         g = self.param_groups[0]
         self.step_count += 1
         ops.sgd_step(self.flat.data, self.flat.grad, self.momentum_buffer, g["lr"], g["momentum"], self.grad_scale,

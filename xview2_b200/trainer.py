@@ -132,6 +132,8 @@ class Trainer:
         optimizer, scheduler = (conf["optimizer"], conf["lr_scheduler"]["scheduler"]) if isinstance(conf, dict) else (conf, None)
         flat = model.flat
         flat.broadcast_params(0)
+        from . import ops
+        ops.enable_wgrad_side_stream(True)  # step()/all_reduce_grads()/zero_grad() below are the sync points
         if resume is not None and resume.get("optimizer"):
             optimizer.load_state_dict(resume["optimizer"])
         for epoch in range(start_epoch, self.max_epochs):
