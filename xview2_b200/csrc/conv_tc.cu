@@ -755,7 +755,9 @@ extern "C" int xv2_conv_tc(const xv2_tc_conv* q, const void* src0, const void* s
   int bk = 0;
   if (q->c0 % 64 == 0 && q->c1 % 64 == 0 && cg % 64 == 0) bk = 64;
   else if (q->c0 % 32 == 0 && q->c1 % 32 == 0 && cg % 32 == 0) bk = 32;
-  const int bn = pick_bn(convt ? q->k : kg);
+  // transposed conv with the TMA-store epilogue: an N tile may span both kw taps of one kh (a contiguous output row segment)
+  const bool convt_wide = convt && q->out_dtype == XV2_BF16 && !bias && (q->ldo == 0 || q->ldo == q->k);
+  const int bn = pick_bn(convt ? (convt_wide ? 2 * q->k : q->k) : kg);
   if (!bk || !bn || (q->out_dtype != XV2_BF16 && q->out_dtype != XV2_F32)) {
     set_error("conv_tc: channels not eligible (c %d+%d k %d groups %d)", q->c0, q->c1, q->k, groups);
     return XV2_EUNSUPPORTED;

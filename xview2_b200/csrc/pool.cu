@@ -2,6 +2,7 @@
 // atomics).  Replaces ATen/cuDNN pooling reached from unet.py:81 (MaxPool2d 3,2,1) and the ResNeSt avd / avg-down
 // pools (unet.py:52).
 #include "common.cuh"
+#include <algorithm>
 
 namespace xv2 {
 
@@ -28,17 +29,14 @@ struct PoolGeom {
   int n, h, w, c, oh, ow, k, stride, pad, cip;
 };
 
-template <typename T, int VEC>
-__global__ void maxpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ idx) {
+template <typename T, int VEC, int KK, int SS>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ idx) {
   const int cv = g.c / VEC;
-  const long long total = (long long)g.n * g.oh * g.ow * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cvi = (int)(i % cv);
-    long long t = i / cv;
-    const int ow = (int)(t % g.ow);
-    t /= g.ow;
-    const int oh = (int)(t % g.oh);
-    const int nb = (int)(t / g.oh);
+  const int K = KK ? KK : g.k, S = SS ? SS : g.stride;  // compile-time for the shapes the U-Nets use
+  const int rowsz = g.ow * cv;  // 32-bit index math: blockIdx.y = (image, row), x runs over (column, channel vector)
+  const int nb = blockIdx.y / g.oh, oh = blockIdx.y - nb * g.oh;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowsz; i += gridDim.x * blockDim.x) {
+    const int ow = i / cv, cvi = i - ow * cv;
     float m[VEC];
     uint8_t am[VEC];  // window position (r*k + s) of the FIRST maximum in scan order, like ATen
 #pragma unroll
@@ -46,11 +44,13 @@ __global__ void maxpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __res
       m[j] = -INFINITY;
       am[j] = 0;
     }
-    for (int r = 0; r < g.k; ++r) {
-      const int ih = oh * g.stride - g.pad + r;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const int ih = oh * S - g.pad + r;
       if (ih < 0 || ih >= g.h) continue;
-      for (int s = 0; s < g.k; ++s) {
-        const int iw = ow * g.stride - g.pad + s;
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        const int iw = ow * S - g.pad + s;
         if (iw < 0 || iw >= g.w) continue;
         float f[VEC];
         pldv<T, VEC>(x + (((long long)nb * g.h + ih) * g.w + iw) * g.c + cvi * VEC, f);
@@ -58,7 +58,7 @@ __global__ void maxpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __res
         for (int j = 0; j < VEC; ++j)
           if (f[j] > m[j]) {
             m[j] = f[j];
-            am[j] = (uint8_t)(r * g.k + s);
+            am[j] = (uint8_t)(r * K + s);
           }
       }
     }
@@ -73,40 +73,38 @@ __global__ void maxpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __res
 
 // dx[n,ih,iw,c] = sum over the windows (oh,ow) containing (ih,iw) whose saved arg-max position is (ih,iw) of dy.
 // Gather form: every dx element is written exactly once, no atomics; reads dy + the uint8 index map only.
-template <typename T, int VEC>
-__global__ void maxpool_bwd_kernel(PoolGeom g, const uint8_t* __restrict__ idx, const T* __restrict__ dy,
+template <typename T, int VEC, int KK, int SS>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(PoolGeom g, const uint8_t* __restrict__ idx, const T* __restrict__ dy,
                                    T* __restrict__ dx) {
   const int cv = g.c / VEC;
-  const long long total = (long long)g.n * g.h * g.w * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cvi = (int)(i % cv);
-    long long t = i / cv;
-    const int iw = (int)(t % g.w);
-    t /= g.w;
-    const int ih = (int)(t % g.h);
-    const int nb = (int)(t / g.h);
+  const int K = KK ? KK : g.k, S = SS ? SS : g.stride;  // compile-time for the shapes the U-Nets use
+  const int rowsz = g.w * cv;  // 32-bit index math: blockIdx.y = (image, row), x runs over (column, channel vector)
+  const int nb = blockIdx.y / g.h, ih = blockIdx.y - nb * g.h;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowsz; i += gridDim.x * blockDim.x) {
+    const int iw = i / cv, cvi = i - iw * cv;
     float acc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-    int oh_lo = (ih + g.pad - g.k + 1 + g.stride - 1);
-    oh_lo = oh_lo < 0 ? 0 : oh_lo / g.stride;
-    int oh_hi = (ih + g.pad) / g.stride;
+    int oh_lo = (ih + g.pad - K + 1 + S - 1);
+    oh_lo = oh_lo < 0 ? 0 : oh_lo / S;
+    int oh_hi = (ih + g.pad) / S;
     if (oh_hi > g.oh - 1) oh_hi = g.oh - 1;
-    int ow_lo = (iw + g.pad - g.k + 1 + g.stride - 1);
-    ow_lo = ow_lo < 0 ? 0 : ow_lo / g.stride;
-    int ow_hi = (iw + g.pad) / g.stride;
+    int ow_lo = (iw + g.pad - K + 1 + S - 1);
+    ow_lo = ow_lo < 0 ? 0 : ow_lo / S;
+    int ow_hi = (iw + g.pad) / S;
     if (ow_hi > g.ow - 1) ow_hi = g.ow - 1;
     for (int oh = oh_lo; oh <= oh_hi; ++oh) {
       for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-        const int mine = (ih - (oh * g.stride - g.pad)) * g.k + (iw - (ow * g.stride - g.pad));
+        const int mine = (ih - (oh * S - g.pad)) * K + (iw - (ow * S - g.pad));
         const long long o = (((long long)nb * g.oh + oh) * g.ow + ow) * g.c + cvi * VEC;
         float d[VEC];
         pldv<T, VEC>(dy + o, d);
         if constexpr (VEC == 8) {
           const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
-          const uint32_t w2[2] = {pk.x, pk.y};
+          const uint32_t pat = (uint32_t)mine * 0x01010101u;
+          const uint32_t m2[2] = {__vcmpeq4(pk.x, pat), __vcmpeq4(pk.y, pat)};  // 0xFF per matching byte
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += (int)((w2[j >> 2] >> (8 * (j & 3))) & 0xFF) == mine ? d[j] : 0.f;
+          for (int j = 0; j < 8; ++j) acc[j] += (m2[j >> 2] >> (8 * (j & 3)) & 1u) ? d[j] : 0.f;
         } else if constexpr (VEC == 4) {
           const uint32_t pk = *reinterpret_cast<const uint32_t*>(idx + o);
 #pragma unroll
@@ -121,9 +119,9 @@ __global__ void maxpool_bwd_kernel(PoolGeom g, const uint8_t* __restrict__ idx, 
   }
 }
 
-__device__ __forceinline__ float avg_divisor(const PoolGeom& g, int oh, int ow) {
-  int hs = oh * g.stride - g.pad, ws = ow * g.stride - g.pad;
-  int he = min(hs + g.k, g.h + g.pad), we = min(ws + g.k, g.w + g.pad);
+__device__ __forceinline__ float avg_divisor(const PoolGeom& g, int oh, int ow, int K, int S) {
+  int hs = oh * S - g.pad, ws = ow * S - g.pad;
+  int he = min(hs + K, g.h + g.pad), we = min(ws + K, g.w + g.pad);
   const int pool = (he - hs) * (we - ws);
   hs = max(hs, 0);
   ws = max(ws, 0);
@@ -132,25 +130,24 @@ __device__ __forceinline__ float avg_divisor(const PoolGeom& g, int oh, int ow) 
   return (float)(g.cip ? pool : (he - hs) * (we - ws));
 }
 
-template <typename T, int VEC>
-__global__ void avgpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __restrict__ y) {
+template <typename T, int VEC, int KK, int SS>
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __restrict__ y) {
   const int cv = g.c / VEC;
-  const long long total = (long long)g.n * g.oh * g.ow * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cvi = (int)(i % cv);
-    long long t = i / cv;
-    const int ow = (int)(t % g.ow);
-    t /= g.ow;
-    const int oh = (int)(t % g.oh);
-    const int nb = (int)(t / g.oh);
+  const int K = KK ? KK : g.k, S = SS ? SS : g.stride;  // compile-time for the shapes the U-Nets use
+  const int rowsz = g.ow * cv;  // 32-bit index math: blockIdx.y = (image, row), x runs over (column, channel vector)
+  const int nb = blockIdx.y / g.oh, oh = blockIdx.y - nb * g.oh;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowsz; i += gridDim.x * blockDim.x) {
+    const int ow = i / cv, cvi = i - ow * cv;
     float a[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) a[j] = 0.f;
-    for (int r = 0; r < g.k; ++r) {
-      const int ih = oh * g.stride - g.pad + r;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const int ih = oh * S - g.pad + r;
       if (ih < 0 || ih >= g.h) continue;
-      for (int s = 0; s < g.k; ++s) {
-        const int iw = ow * g.stride - g.pad + s;
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        const int iw = ow * S - g.pad + s;
         if (iw < 0 || iw >= g.w) continue;
         float f[VEC];
         pldv<T, VEC>(x + (((long long)nb * g.h + ih) * g.w + iw) * g.c + cvi * VEC, f);
@@ -158,40 +155,37 @@ __global__ void avgpool_fwd_kernel(PoolGeom g, const T* __restrict__ x, T* __res
         for (int j = 0; j < VEC; ++j) a[j] += f[j];
       }
     }
-    const float inv = 1.0f / avg_divisor(g, oh, ow);
+    const float inv = 1.0f / avg_divisor(g, oh, ow, K, S);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) a[j] *= inv;
     pstv<T, VEC>(y + (((long long)nb * g.oh + oh) * g.ow + ow) * g.c + cvi * VEC, a);
   }
 }
 
-template <typename T, int VEC>
-__global__ void avgpool_bwd_kernel(PoolGeom g, const T* __restrict__ dy, T* __restrict__ dx) {
+template <typename T, int VEC, int KK, int SS>
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(PoolGeom g, const T* __restrict__ dy, T* __restrict__ dx) {
   const int cv = g.c / VEC;
-  const long long total = (long long)g.n * g.h * g.w * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cvi = (int)(i % cv);
-    long long t = i / cv;
-    const int iw = (int)(t % g.w);
-    t /= g.w;
-    const int ih = (int)(t % g.h);
-    const int nb = (int)(t / g.h);
+  const int K = KK ? KK : g.k, S = SS ? SS : g.stride;  // compile-time for the shapes the U-Nets use
+  const int rowsz = g.w * cv;  // 32-bit index math: blockIdx.y = (image, row), x runs over (column, channel vector)
+  const int nb = blockIdx.y / g.h, ih = blockIdx.y - nb * g.h;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowsz; i += gridDim.x * blockDim.x) {
+    const int iw = i / cv, cvi = i - iw * cv;
     float acc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-    int oh_lo = (ih + g.pad - g.k + 1 + g.stride - 1);
-    oh_lo = oh_lo < 0 ? 0 : oh_lo / g.stride;
-    int oh_hi = (ih + g.pad) / g.stride;
+    int oh_lo = (ih + g.pad - K + 1 + S - 1);
+    oh_lo = oh_lo < 0 ? 0 : oh_lo / S;
+    int oh_hi = (ih + g.pad) / S;
     if (oh_hi > g.oh - 1) oh_hi = g.oh - 1;
-    int ow_lo = (iw + g.pad - g.k + 1 + g.stride - 1);
-    ow_lo = ow_lo < 0 ? 0 : ow_lo / g.stride;
-    int ow_hi = (iw + g.pad) / g.stride;
+    int ow_lo = (iw + g.pad - K + 1 + S - 1);
+    ow_lo = ow_lo < 0 ? 0 : ow_lo / S;
+    int ow_hi = (iw + g.pad) / S;
     if (ow_hi > g.ow - 1) ow_hi = g.ow - 1;
     for (int oh = oh_lo; oh <= oh_hi; ++oh)
       for (int ow = ow_lo; ow <= ow_hi; ++ow) {
         float d[VEC];
         pldv<T, VEC>(dy + (((long long)nb * g.oh + oh) * g.ow + ow) * g.c + cvi * VEC, d);
-        const float inv = 1.0f / avg_divisor(g, oh, ow);
+        const float inv = 1.0f / avg_divisor(g, oh, ow, K, S);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] = fmaf(d[j], inv, acc[j]);
       }
@@ -209,15 +203,18 @@ static int pool_blocks(long long total) {
 
 using namespace xv2;
 
-#define XV2_POOL_LAUNCH(KERNEL, total_pixels, ...)                                              \
+#define XV2_POOL_LAUNCH(KERNEL, images, rows, cols, ...)                                        \
   do {                                                                                          \
     const int vecw = (dtype == XV2_BF16 ? 8 : 4);                                               \
     const bool use_vec = (c % vecw) == 0;                                                       \
-    const long long total = (long long)(total_pixels) * (use_vec ? c / vecw : c);               \
-    const int blocks = pool_blocks(total);                                                      \
+    const long long rowsz = (long long)(cols) * (use_vec ? c / vecw : c);                       \
+    XV2_REQUIRE((long long)(images) * (rows) <= 65535 && rowsz < (1LL << 30), "pool: tensor too large for the 2-D grid"); \
+    const dim3 grid((unsigned)std::min<long long>(cdiv(rowsz, 256), 64), (unsigned)((images) * (rows)));            \
     XV2_DISPATCH_DTYPE(dtype, T, {                                                              \
-      if (use_vec) KERNEL<T, Vec<T>::N><<<blocks, 256, 0, as_stream(stream)>>>(__VA_ARGS__);    \
-      else KERNEL<T, 1><<<blocks, 256, 0, as_stream(stream)>>>(__VA_ARGS__);                    \
+      if (use_vec && k == 3 && stride == 2) KERNEL<T, Vec<T>::N, 3, 2><<<grid, 256, 0, as_stream(stream)>>>(__VA_ARGS__); \
+      else if (use_vec && k == 2 && stride == 2) KERNEL<T, Vec<T>::N, 2, 2><<<grid, 256, 0, as_stream(stream)>>>(__VA_ARGS__); \
+      else if (use_vec) KERNEL<T, Vec<T>::N, 0, 0><<<grid, 256, 0, as_stream(stream)>>>(__VA_ARGS__); \
+      else KERNEL<T, 1, 0, 0><<<grid, 256, 0, as_stream(stream)>>>(__VA_ARGS__);                \
     });                                                                                         \
     XV2_LAUNCH_CHECK();                                                                         \
   } while (0)
@@ -227,7 +224,7 @@ extern "C" int xv2_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t n, 
                                void* stream) {
   XV2_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0 && k > 0 && k <= 15 && stride > 0, "maxpool: bad shape");
   PoolGeom g{n, h, w, c, oh, ow, k, stride, pad, 0};
-  XV2_POOL_LAUNCH(maxpool_fwd_kernel, (long long)n * oh * ow, g, (const T*)x, (T*)y, idx);
+  XV2_POOL_LAUNCH(maxpool_fwd_kernel, n, oh, ow, g, (const T*)x, (T*)y, idx);
   return XV2_OK;
 }
 extern "C" int xv2_maxpool_bwd(const uint8_t* idx, const void* dy, void* dx, int32_t n, int32_t h, int32_t w,
@@ -236,7 +233,7 @@ extern "C" int xv2_maxpool_bwd(const uint8_t* idx, const void* dy, void* dx, int
   XV2_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0 && k > 0 && stride > 0, "maxpool: bad shape");
   XV2_REQUIRE(idx != nullptr, "maxpool_bwd: index map missing");
   PoolGeom g{n, h, w, c, oh, ow, k, stride, pad, 0};
-  XV2_POOL_LAUNCH(maxpool_bwd_kernel, (long long)n * h * w, g, idx, (const T*)dy, (T*)dx);
+  XV2_POOL_LAUNCH(maxpool_bwd_kernel, n, h, w, g, idx, (const T*)dy, (T*)dx);
   return XV2_OK;
 }
 extern "C" int xv2_avgpool_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh,
@@ -244,7 +241,7 @@ extern "C" int xv2_avgpool_fwd(const void* x, void* y, int32_t n, int32_t h, int
                                int32_t dtype, void* stream) {
   XV2_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0 && k > 0 && stride > 0, "avgpool: bad shape");
   PoolGeom g{n, h, w, c, oh, ow, k, stride, pad, count_include_pad};
-  XV2_POOL_LAUNCH(avgpool_fwd_kernel, (long long)n * oh * ow, g, (const T*)x, (T*)y);
+  XV2_POOL_LAUNCH(avgpool_fwd_kernel, n, oh, ow, g, (const T*)x, (T*)y);
   return XV2_OK;
 }
 extern "C" int xv2_avgpool_bwd(const void* dy, void* dx, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh,
@@ -252,6 +249,6 @@ extern "C" int xv2_avgpool_bwd(const void* dy, void* dx, int32_t n, int32_t h, i
                                int32_t dtype, void* stream) {
   XV2_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0 && k > 0 && stride > 0, "avgpool: bad shape");
   PoolGeom g{n, h, w, c, oh, ow, k, stride, pad, count_include_pad};
-  XV2_POOL_LAUNCH(avgpool_bwd_kernel, (long long)n * h * w, g, (const T*)dy, (T*)dx);
+  XV2_POOL_LAUNCH(avgpool_bwd_kernel, n, h, w, g, (const T*)dy, (T*)dx);
   return XV2_OK;
 }

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const __nv_bfloat1
   constexpr int TP = 64;                       // output pixels per tile (a segment of one output row)
   constexpr int XW = (2 * TP + 1) * 3;         // input values per patch row: columns 2*ox0 - 1 .. 2*ox0 + 2*TP - 1, 3 channels
   __shared__ float red[27][K];
-  __shared__ __align__(16) __nv_bfloat16 dys[TP][K];
+  __shared__ __align__(16) float dys[TP][K];  // dy tile converted to fp32 once, so the inner loop is LDS.128 + FFMA only
   __shared__ float xs[3][XW];
   for (int i = threadIdx.x; i < 27 * K; i += blockDim.x) red[i / K][i % K] = 0.f;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -89,7 +89,13 @@ __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const __nv_bfloat1
       const int px = i / (K / 8), v = i % (K / 8);
       uint4 q = make_uint4(0, 0, 0, 0);
       if (px < npx) q = __ldg(reinterpret_cast<const uint4*>(dy + (((long long)img * oh + oy) * ow + ox0 + px) * K) + v);
-      *reinterpret_cast<uint4*>(&dys[px][v * 8]) = q;
+      const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+      float4 lo = make_float4(__uint_as_float(wds[0] << 16), __uint_as_float(wds[0] & 0xffff0000u), __uint_as_float(wds[1] << 16),
+                              __uint_as_float(wds[1] & 0xffff0000u));
+      float4 hi = make_float4(__uint_as_float(wds[2] << 16), __uint_as_float(wds[2] & 0xffff0000u), __uint_as_float(wds[3] << 16),
+                              __uint_as_float(wds[3] & 0xffff0000u));
+      *reinterpret_cast<float4*>(&dys[px][v * 8]) = lo;
+      *reinterpret_cast<float4*>(&dys[px][v * 8 + 4]) = hi;
     }
     for (int i = threadIdx.x; i < 3 * XW; i += blockDim.x) {
       const int rr = i / XW, j = i % XW;
@@ -101,16 +107,14 @@ __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const __nv_bfloat1
     __syncthreads();
     for (int px = warp; px < npx; px += 8) {
       const float xv = xs[r][(2 * px + s) * 3 + c];
-      const uint4* g = reinterpret_cast<const uint4*>(&dys[px][0]);
+      const float4* g = reinterpret_cast<const float4*>(&dys[px][0]);
 #pragma unroll
-      for (int v = 0; v < K / 8; ++v) {
-        const uint4 q = g[v];
-        const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc[v * 8 + 2 * i] = fmaf(xv, __uint_as_float(wds[i] << 16), acc[v * 8 + 2 * i]);
-          acc[v * 8 + 2 * i + 1] = fmaf(xv, __uint_as_float(wds[i] & 0xffff0000u), acc[v * 8 + 2 * i + 1]);
-        }
+      for (int v = 0; v < K / 4; ++v) {
+        const float4 q = g[v];
+        acc[v * 4] = fmaf(xv, q.x, acc[v * 4]);
+        acc[v * 4 + 1] = fmaf(xv, q.y, acc[v * 4 + 1]);
+        acc[v * 4 + 2] = fmaf(xv, q.z, acc[v * 4 + 2]);
+        acc[v * 4 + 3] = fmaf(xv, q.w, acc[v * 4 + 3]);
       }
     }
   }
