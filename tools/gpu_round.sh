@@ -17,7 +17,7 @@ for s in $STAGES; do
     launches) timeout 1200 $NCU --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
         --log-file gpurun_out/launches.csv python tools/layer_profile.py --ncu > gpurun_out/launches.log 2>&1; wc -l gpurun_out/launches.csv ;;
     ncu_conv) timeout 1200 $NCU --set full --clock-control none --import-source on --profile-from-start off \
-        -k regex:conv_tc_kernel -s 40 -c 3 -f -o gpurun_out/prof_conv python tools/layer_profile.py --ncu > gpurun_out/ncu_conv.log 2>&1; tail -3 gpurun_out/ncu_conv.log ;;
+        -k regex:conv_tc_kernel -s 0 -c 4 -f -o gpurun_out/prof_conv python tools/layer_profile.py --ncu > gpurun_out/ncu_conv.log 2>&1; tail -3 gpurun_out/ncu_conv.log ;;
     ncu_strip) timeout 1200 $NCU --set full --clock-control none --import-source on --profile-from-start off \
         -k regex:conv_strip_kernel -c 8 -f -o gpurun_out/prof_strip python tools/layer_profile.py --ncu > gpurun_out/ncu_strip.log 2>&1; tail -3 gpurun_out/ncu_strip.log ;;
     ncu_bn) timeout 1200 $NCU --set full --clock-control none --import-source on --profile-from-start off \

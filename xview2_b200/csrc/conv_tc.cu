@@ -275,38 +275,40 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           bulk_commit();
         }
         if (p.stats) {
-          // column sums of the staged (rounded) tile: 128 threads = column pairs x row groups, conflict-free LDS.32
-          const int t = q * 32 + lane;
-          int cp, r0;
-          if (p.store_c == 64) {
-            cp = t & 31;
-            r0 = t >> 5;        // rows r0, r0 + 4, ...
-          } else {
-            cp = t & 15;
-            const int rg = t >> 4;
-            r0 = rg;            // rows r0, r0 + 8, ...: lanes 0-15 / 16-31 read adjacent rows (different banks)
-          }
+          // Column sums of the staged (rounded) tile WITHOUT atomics: warp wq of the half owns 8 (4) column pairs; its lanes
+          // split the rows so that one LDS.32 touches every bank once (the row offsets below undo the TMA swizzle), shuffles
+          // fold the row groups, and the owning lanes add into the CTA's statistics (each channel has exactly one owner).
+          const int wq = (warp - 2) & 3;
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-          // rows r0 + 8 i (+ 4 for 128-byte rows): the swizzle term repeats every 8 rows, so the addresses are base + i * stride
-          const uint32_t inrow = ((uint32_t)(cp & 3) << 2);
-          const uint32_t sw0 = p.store_c == 64 ? (uint32_t)(r0 & 7) : (uint32_t)((r0 >> 1) & 3);
-          const uint32_t a0 = sbuf + r0 * rowb + ((((uint32_t)cp >> 2) ^ sw0) << 4) + inrow;
-          const uint32_t a1 = sbuf + (r0 + 4) * rowb + ((((uint32_t)cp >> 2) ^ (uint32_t)((r0 + 4) & 7)) << 4) + inrow;
-          const uint32_t stride = 8 * rowb;
-          uint32_t wv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[i]) : "r"(a0 + i * stride));
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float a = __uint_as_float(wv[i] << 16), b = __uint_as_float(wv[i] & 0xffff0000u);
-            s0 += a;
-            s1 += b;
-            q0 = fmaf(a, a, q0);
-            q1 = fmaf(b, b, q1);
-          }
+          int cp, nfold;
           if (p.store_c == 64) {
+            const int cpl = lane & 7, rg = lane >> 3;  // 4 row groups: rows 2 rg + 8 i (+ 1)
+            cp = wq * 8 + cpl;
+            nfold = 2;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[i]) : "r"(a1 + i * stride));
+            for (int par = 0; par < 2; ++par) {
+              const int r0 = 2 * rg + par;
+              const uint32_t a0 = sbuf + r0 * 128 + ((((uint32_t)cp >> 2) ^ (uint32_t)(r0 & 7)) << 4) + ((cp & 3) << 2);
+              uint32_t wv[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[i]) : "r"(a0 + i * 1024));
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float a = __uint_as_float(wv[i] << 16), b = __uint_as_float(wv[i] & 0xffff0000u);
+                s0 += a;
+                s1 += b;
+                q0 = fmaf(a, a, q0);
+                q1 = fmaf(b, b, q1);
+              }
+            }
+          } else {
+            const int cpl = lane & 3, rg = lane >> 2;  // 8 row groups: rows rg + 8 i
+            cp = wq * 4 + cpl;
+            nfold = 3;
+            const uint32_t a0 = sbuf + rg * 64 + ((((uint32_t)cp >> 2) ^ (uint32_t)((rg >> 1) & 3)) << 4) + ((cp & 3) << 2);
+            uint32_t wv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[i]) : "r"(a0 + i * 512));
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float a = __uint_as_float(wv[i] << 16), b = __uint_as_float(wv[i] & 0xffff0000u);
@@ -316,11 +318,20 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
               q1 = fmaf(b, b, q1);
             }
           }
-          const uint32_t sa = stats_sm + 4 * (co0 + sb * p.store_c + 2 * cp);
-          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa), "f"(s0) : "memory");
-          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa + 4), "f"(s1) : "memory");
-          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa + 4 * p.k_total), "f"(q0) : "memory");
-          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa + 4 * p.k_total + 4), "f"(q1) : "memory");
+          for (int f = 0, o = 16; f < nfold; ++f, o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+          }
+          if (lane < (p.store_c == 64 ? 8 : 4)) {
+            const uint32_t sa = stats_sm + 4 * (co0 + sb * p.store_c + 2 * cp);
+            float v0, v1, v2, v3;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v0), "=f"(v1) : "r"(sa));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v2), "=f"(v3) : "r"(sa + 4 * p.k_total));
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa), "f"(v0 + s0), "f"(v1 + s1) : "memory");
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa + 4 * p.k_total), "f"(v2 + q0), "f"(v3 + q1) : "memory");
+          }
         }
       }
       tc_fence_before();
