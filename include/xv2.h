@@ -122,6 +122,11 @@ typedef struct xv2_tc_conv {
 int xv2_conv_tc(const xv2_tc_conv* p, const void* src0, const void* src1, const void* w, const float* bias,
                 void* out, double* stats, void* stream);
 
+/* Inference form: eval-mode BatchNorm (+ activation) folded into the conv epilogue, out = act(scale[k] * conv + shift[k])
+ * with scale / shift from xv2_bn_eval_coeffs (layers.py:92-94 in eval mode: no separate BN pass at all). */
+int xv2_conv_tc_bnact(const xv2_tc_conv* p, const void* src0, const void* src1, const void* w, const float* scale,
+                      const float* shift, int32_t act, void* out, void* stream);
+
 /* Tensor-core weight gradient: dw[k][r][s][c] fp32 (accumulated with atomics; caller zero-fills), bf16 operands.
  * src0/src1 as above (c split the same way), dout [n][h][w][k] with pixel stride lddo (0 = k).
  * convt = 1: dw is [c0(row)][2][2][k]: gradient of the transposed conv given x = src0 (n,h,w,c0), dout (n,2h,2w,k). */

@@ -42,6 +42,9 @@ struct alignas(64) StripParams {
   long long rows_total;     // wsets * n * wtiles * h
   __nv_bfloat16* out;
   double* stats;            // optional [2 * k_total]
+  const float* ep_scale;    // optional inference epilogue: y = act(ep_scale[k] * conv + ep_shift[k])
+  const float* ep_shift;
+  int ep_act;
 };
 
 struct Piece {
@@ -250,7 +253,13 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
             uint32_t w4[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              __nv_bfloat162 hp = __floats2bfloat162_rn(__uint_as_float(v[j + 2 * t]), __uint_as_float(v[j + 2 * t + 1]));
+              float a = __uint_as_float(v[j + 2 * t]), b = __uint_as_float(v[j + 2 * t + 1]);
+              if (p.ep_scale) {
+                const int ch = co0 + c0 + j + 2 * t;
+                a = apply_act(fmaf(a, p.ep_scale[ch], p.ep_shift[ch]), p.ep_act);
+                b = apply_act(fmaf(b, p.ep_scale[ch + 1], p.ep_shift[ch + 1]), p.ep_act);
+              }
+              __nv_bfloat162 hp = __floats2bfloat162_rn(a, b);
               w4[t] = *reinterpret_cast<uint32_t*>(&hp);
               f[j + 2 * t] = __uint_as_float(w4[t] << 16);
               f[j + 2 * t + 1] = __uint_as_float(w4[t] & 0xffff0000u);
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
 
 // Host side.  Returns XV2_EUNSUPPORTED when the shape is not a strip shape (caller uses the tile-per-tap kernel).
 int conv_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, const void* w, void* out, double* stats,
-                      void* stream) {
+                      const float* ep_scale, const float* ep_shift, int ep_act, void* stream) {
   const int groups = q->groups < 1 ? 1 : q->groups;
   const int ld0 = q->ld0 ? q->ld0 : q->c0, ld1 = q->ld1 ? q->ld1 : q->c1;
   const int ctot = q->c0 + q->c1;
@@ -364,6 +373,9 @@ int conv_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, 
   p.rows_total = (long long)groups * p.n_tiles * q->n * p.wtiles * q->h;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.stats = stats;
+  p.ep_scale = ep_scale;
+  p.ep_shift = ep_shift;
+  p.ep_act = ep_act;
   const uint32_t wb = ((9u * chunks * bn * rowb) + 1023u) & ~1023u;
   const size_t smem = 1024 + wb + (size_t)ring * slot_bytes + 512 + 1024 + 2 * 8192;
   long long grid = tc_num_sms();

@@ -78,6 +78,10 @@ struct alignas(64) TcParams {
   int tma_store;           // 0: direct register -> global stores
   int store_c;             // channels per staged block (64 -> 128B swizzle, 32 -> 64B swizzle)
   double* stats;           // optional fp64 [2 * k_total]: BN sum / sum of squares of the rounded outputs
+  // optional inference epilogue: y = act(ep_scale[k] * conv + ep_shift[k])  (eval-mode BatchNorm + activation folded in)
+  const float* ep_scale;
+  const float* ep_shift;
+  int ep_act;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -256,6 +260,11 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
               if (p.bias) {
                 a += p.bias[co0 + col + j + 2 * i];
                 b += p.bias[co0 + col + j + 2 * i + 1];
+              }
+              if (p.ep_scale) {
+                const int ch = co0 + col + j + 2 * i;
+                a = apply_act(fmaf(a, p.ep_scale[ch], p.ep_shift[ch]), p.ep_act);
+                b = apply_act(fmaf(b, p.ep_scale[ch + 1], p.ep_shift[ch + 1]), p.ep_act);
               }
               __nv_bfloat162 hp = __floats2bfloat162_rn(a, b);
               w4[i] = *reinterpret_cast<uint32_t*>(&hp);
@@ -669,7 +678,7 @@ int strip_encode_weight(CUtensorMap* m, const void* ptr, long long rows, long lo
 }
 int tc_num_sms() { return g_num_sms; }
 int conv_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, const void* w, void* out, double* stats,
-                      void* stream);
+                      const float* ep_scale, const float* ep_shift, int ep_act, void* stream);
 int wgrad_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, const void* dout, int lddo, float* dw,
                        void* stream);
 static bool strip_enabled() {
@@ -742,13 +751,27 @@ extern "C" int xv2_init(int device) {
 }
 
 // p->gather flag is carried in `convt` = 2 (transposed-conv data gradient: src0 is (n, 2h, 2w, c0), taps 2x2)
+static int conv_tc_impl(const xv2_tc_conv* q, const void* src0, const void* src1, const void* w, const float* bias,
+                        void* out, double* stats, const float* ep_scale, const float* ep_shift, int ep_act, void* stream);
+
 extern "C" int xv2_conv_tc(const xv2_tc_conv* q, const void* src0, const void* src1, const void* w,
                            const float* bias, void* out, double* stats, void* stream) {
+  return conv_tc_impl(q, src0, src1, w, bias, out, stats, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int xv2_conv_tc_bnact(const xv2_tc_conv* q, const void* src0, const void* src1, const void* w, const float* scale,
+                                 const float* shift, int32_t act, void* out, void* stream) {
+  XV2_REQUIRE(scale && shift, "conv_tc_bnact: null coefficients");
+  return conv_tc_impl(q, src0, src1, w, nullptr, out, nullptr, scale, shift, act, stream);
+}
+
+static int conv_tc_impl(const xv2_tc_conv* q, const void* src0, const void* src1, const void* w, const float* bias,
+                        void* out, double* stats, const float* ep_scale, const float* ep_shift, int ep_act, void* stream) {
   XV2_REQUIRE(q && src0 && w && out, "conv_tc: null argument");
   int rc = ensure_init();
   if (rc) return rc;
   if (!bias && strip_enabled()) {
-    rc = conv_strip_launch(q, src0, src1, w, out, stats, stream);
+    rc = conv_strip_launch(q, src0, src1, w, out, stats, ep_scale, ep_shift, ep_act, stream);
     if (rc != XV2_EUNSUPPORTED) return rc;
   }
   const int groups = q->groups < 1 ? 1 : q->groups;
@@ -822,6 +845,12 @@ extern "C" int xv2_conv_tc(const xv2_tc_conv* q, const void* src0, const void* s
     if (rc) return rc;
     extra = 1024 + 2 * 16384 + (stats ? 8u * q->k : 0u);
     p.stats = stats;
+    p.ep_scale = ep_scale;
+    p.ep_shift = ep_shift;
+    p.ep_act = ep_act;
+  } else if (ep_scale) {
+    set_error("conv_tc_bnact: shape not served by the TMA-store epilogue");
+    return XV2_EUNSUPPORTED;
   }
   const uint32_t stage_bytes = 128u * bk * 2 + (uint32_t)bn * bk * 2;
   int stages = (int)((kSmemBudget - extra) / stage_bytes);

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "xv2_pack_weight": [P, P, I32, I32, I32, I32, I32, I32, I32, P],
     "xv2_pack_weights_batched": [P, I32, P],
     "xv2_conv_tc": [POINTER(TcConv), P, P, P, P, P, P, P],
+    "xv2_conv_tc_bnact": [POINTER(TcConv), P, P, P, P, P, I32, P, P],
     "xv2_wgrad_tc": [POINTER(TcConv), P, P, P, I32, P, P],
     "xv2_bn_stats": [P, I64, I32, I32, P, P],
     "xv2_bn_finalize": [P, I64, I32, P, P, P, P, F, F, P, P, P, P, P],

@@ -502,10 +502,55 @@ def batch_norm_act(x, bn, act=ACT_NONE, residual=None, stats=None):
                                bn.momentum if bn.momentum is not None else 0.1, bn.eps, act, stats if use_batch else None)
 
 
+def _eval_coeffs(bn):
+    """(scale, shift) of an eval-mode BatchNorm, cached on the module until its parameters / running statistics change."""
+    stamp = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, _pack_epoch,
+             bn.weight.data_ptr())
+    hit = bn.__dict__.get("_xv2_eval")
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    c = bn.num_features
+    coef = torch.empty(2, c, dtype=torch.float32, device=bn.weight.device)
+    call("xv2_bn_eval_coeffs", c, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps),
+         ptr(coef[0]), ptr(coef[1]))
+    bn.__dict__["_xv2_eval"] = (stamp, coef)
+    return coef
+
+
+def _conv_bnact_inference(x, conv, bn, act, x2):
+    """Inference (no autograd, eval-mode BN): BatchNorm + activation folded into the conv epilogue -- no BN pass at all.
+    Returns None when the tensor-core kernels do not serve the shape."""
+    stride, pad, dil, groups = conv.stride[0], conv.padding[0], conv.dilation[0], conv.groups
+    if not (_tc_ok(x) and stride == 1 and conv.bias is None):
+        return None
+    x = nhwc(x)
+    n, c0, h, w = x.shape
+    c1 = 0
+    if x2 is not None:
+        x2 = nhwc(x2)
+        c1 = x2.shape[1]
+    k, cg, r, s = conv.weight.shape
+    if _out_size(h, r, 1, pad, dil) != h or _out_size(w, s, 1, pad, dil) != w:
+        return None
+    coef = _eval_coeffs(bn)
+    wp = pack_weight(conv.weight, 0, torch.bfloat16, groups)
+    out = empty_act(n, k, h, w, x.dtype, x.device)
+    p = TcConv(n, h, w, c0, c1, 0, 0, k, r, s, pad, dil, groups, 0, BF16, 0)
+    lib.note_work(2.0 * n * h * w * k * cg * r * s, 2.0 * n * h * w * (c0 + c1 + k) + 2.0 * k * cg * r * s,
+                  f"fwd+bn n{n} {h}x{w} c{c0}+{c1} k{k} {r}x{s} g{groups}")
+    rc = call("xv2_conv_tc_bnact", p, ptr(x), ptr(x2), ptr(wp), ptr(coef[0]), ptr(coef[1]), act, ptr(out), allow_unsupported=True)
+    return out if rc == 0 else None
+
+
 def conv_bn_act(x, conv, bn, act=ACT_NONE, x2=None, residual=None):
     """conv -> BatchNorm -> activation (+ residual) for an nn.Conv2d / nn.BatchNorm2d parameter pair; in training the BN
-    statistics come out of the conv epilogue when the kernel supports it."""
+    statistics come out of the conv epilogue when the kernel supports it; at inference (eval-mode BN, autograd off) the
+    BatchNorm and the activation are folded into the conv epilogue."""
     args = (x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0], conv.groups, x2)
+    if not bn.training and bn.track_running_stats and residual is None and not torch.is_grad_enabled():
+        out = _conv_bnact_inference(x, conv, bn, act, x2)
+        if out is not None:
+            return out
     if bn.training or not bn.track_running_stats:
         out, stats = conv2d_stats(*args)
     else:
