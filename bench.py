@@ -35,6 +35,15 @@ def config_namespace(a):
         epochs=1, gpus=a.gpus, init_lr=1e-4, final_lr=1e-4, results=None, logname="bench", autoaugment=False)
 
 
+def workload_config(batch, size, world):
+    """The `config` object of BOTH arms (ours and --impl reference): BASELINE.json configs[1]."""
+    return {"workload": f"ResNeSt-50 U-Net --type pre, batch {batch}/GPU, {size}x{size}x3 synthetic tiles, bf16 compute / fp32 master "
+                        f"weights, focal+dice loss, forward + backward + fused AdamW step (BASELINE.json configs[1])",
+            "global_batch": batch * world,
+            "parallelism": f"dp{world}: tiles sharded over ranks, one NCCL all-reduce of the flat gradient buffer",
+            "l2": "activations per step (tens of GB) exceed the 126 MB L2; no explicit flush needed"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -152,9 +161,10 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ResNeSt-50 U-Net --type pre, focal+dice, fwd+bwd, CPU PyTorch path of the reference "
-                                   "(oracle port; /root/reference needs pytorch_lightning/apex/monai/resnest and cannot be installed)",
-                       "sample": sample},
+            "config": dict(workload_config(a.batch, a.size, max(1, a.gpus)),
+                           reference_impl="CPU PyTorch path of the reference, fp32, all host cores (oracle port: /root/reference is a "
+                                          "script tree whose pytorch_lightning / apex / monai / resnest imports cannot be installed)",
+                           reference_sample=sample),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -248,14 +258,27 @@ def run_ours(a):
         float(train_step(batch).detach())
         ring.release(i)
     fence()
+    # The loss of EVERY step is read back on the host inside the timed region, one step behind the launch front (the read of
+    # step i is issued after step i+1 has been enqueued), so the device never waits for Python between steps.
+    pinned_loss = torch.empty(a.steps, dtype=torch.float32).pin_memory()
+    host_losses = []
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for i in range(2, 2 + a.steps):
+    pending = None
+    for j, i in enumerate(range(2, 2 + a.steps)):
         ring.submit(i + 1)           # next batch's copy overlaps this step
         batch = ring.acquire(i)
         l = train_step(batch)
         ring.release(i)
-        _ = float(l.detach())        # D2H read of the step's result
+        pinned_loss[j:j + 1].copy_(l.detach().reshape(1), non_blocking=True)  # D2H of this step's result
+        done = torch.cuda.Event()
+        done.record()
+        if pending is not None:
+            pending[1].synchronize()
+            host_losses.append(float(pinned_loss[pending[0]]))
+        pending = (j, done)
+    pending[1].synchronize()
+    host_losses.append(float(pinned_loss[pending[0]]))
     e3.record()
     fence()
     clocks = sampler.stop() if sampler else None
@@ -315,12 +338,10 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"ResNeSt-50 U-Net --type pre, batch {B}/GPU, {S}x{S}x3 synthetic tiles, bf16 compute / fp32 master "
-                                   f"weights, focal+dice loss, forward + backward + fused AdamW step (BASELINE.json configs[1])",
-                       "global_batch": B * world, "parallelism": f"dp{world}: tiles sharded over ranks, one NCCL all-reduce of the flat gradient buffer",
-                       "l2": "activations per step (tens of GB) exceed the 126 MB L2; no explicit flush needed"},
+            "config": workload_config(B, S, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ring.bytes_per_batch, "d2h_bytes_per_step": 4,
-                    "path": "pinned uint8 HWC tiles + masks -> side-stream H2D (double-buffered TileRing) -> Model.training_step -> backward -> all-reduce -> AdamW -> loss.item()"},
+                    "path": "pinned uint8 HWC tiles + masks -> side-stream H2D (double-buffered TileRing) -> Model.training_step -> backward -> all-reduce -> AdamW -> loss D2H into pinned memory, read on the host every step (one step behind the launch front)",
+                    "losses_read": len(host_losses)},
             "gpu_launches": launches,
             "conv_roofline_frac": round(FWD_BWD_GFLOP_PER_TILE * value / 1e3 / peaks["tensor"], 4),
             "roofline": roof, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": kernels, "loss": last_loss,
