@@ -122,7 +122,13 @@ def last_error():
     return load().xv2_last_error().decode()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (raw C accessor: no Stream object per launch)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -170,7 +176,7 @@ def profile_stop(per_call=False):
 def call(name, *args, allow_unsupported=False):
     """Calls an entry point with the current stream appended; raises Xv2Error on failure."""
     global _launches, _work
-    lib = load()
+    lib = _lib if _lib is not None else load()
     if _profile is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
