@@ -41,7 +41,8 @@ def workload_config(batch, size, world):
                         f"weights, focal+dice loss, forward + backward + fused AdamW step (BASELINE.json configs[1])",
             "global_batch": batch * world,
             "parallelism": f"dp{world}: tiles sharded over ranks, one NCCL all-reduce of the flat gradient buffer",
-            "l2": "activations per step (tens of GB) exceed the 126 MB L2; no explicit flush needed"}
+            "l2": "activations per step (tens of GB) exceed the 126 MB L2; no explicit flush needed",
+            "launch": "forward + backward replayed from one CUDA graph; gradient all-reduce, fused AdamW and weight re-pack eager"}
 
 
 def measured_peaks():
@@ -231,6 +232,14 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    eager_step = train_step
+    use_graph = os.environ.get("XV2_NO_GRAPH", "0") != "1"
+    if use_graph:
+        # forward + backward captured once in a CUDA graph and replayed; all-reduce + fused AdamW + re-pack stay eager
+        from xview2_b200.graph import GraphedTrainStep
+        gstep = GraphedTrainStep(model, opt, resident, warmup=2)
+        train_step = gstep  # same signature: batch -> loss tensor
+
     # ---- device-resident throughput ("value") ------------------------------------------------------------------
     for _ in range(a.warmup):
         train_step(resident)
@@ -292,7 +301,7 @@ def run_ours(a):
     roof = kernels = None
     if rank == 0:
         lib.profile_start()
-    train_step(resident)
+    eager_step(resident)
     fence()
     if rank == 0:
         prof = lib.profile_stop()

@@ -128,3 +128,60 @@ def test_bf16_parity(name):
     print(f"\n[bf16 {name}] eval logits {err:.4f} (torch autocast {amp_eval:.4f}) train logits {terr:.4f} "
           f"(torch autocast {amp_train:.4f}) loss {lerr:.5f} argmax agreement {agree:.4f}")
     assert err < max(6e-2, 1.5 * amp_eval) and terr < max(6e-2, 1.5 * amp_train) and lerr < 3e-2
+
+
+def test_cuda_graph_step_matches_eager():
+    """xview2_b200.graph.GraphedTrainStep: replaying forward + backward from a CUDA graph trains like the eager step."""
+    import argparse
+
+    from xview2_b200.graph import GraphedTrainStep
+    from xview2_b200.model.plt import Model
+
+    ns = argparse.Namespace(ppm=False, aspp=False, dilation=1, no_skip=False, interpolate=False, attention=False, dec_interp=False,
+                            deep_supervision=False, loss_str="focal+dice", encoder="resnest50", dmg_model="siamese", type="pre",
+                            tta=False, precision="bf16", lr=1e-3, optimizer="sgd", weight_decay=0.0, momentum=0.9,
+                            use_scheduler=False, warmup=1, epochs=1, gpus=1, init_lr=1e-4, final_lr=1e-4, results=None,
+                            logname="t", autoaugment=False)
+    g = torch.Generator().manual_seed(3)
+    batches = [{"tiles": torch.randint(0, 256, (4, 128, 128, 3), generator=g, dtype=torch.uint8).cuda(),
+                "mask": torch.randint(0, 2, (4, 16, 16), generator=g, dtype=torch.uint8).repeat_interleave(8, 1)
+                .repeat_interleave(8, 2).contiguous().cuda()} for _ in range(4)]
+
+    def run(graphed):
+        torch.manual_seed(5)
+        model = Model(ns).cuda().train()
+        opt = model.configure_optimizers()
+        losses = []
+        step = None
+        stream = torch.cuda.Stream()  # eager steps and the capture share one non-default stream (see xview2_b200/graph.py)
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            for i, b in enumerate(batches * 2):
+                if graphed and i >= 1:
+                    if step is None:
+                        step = GraphedTrainStep(model, opt, b, warmup=0, stream=stream)
+                    losses.append(float(step(b)))
+                else:
+                    opt.zero_grad()
+                    loss = model.training_step(b, i)
+                    loss.backward()
+                    opt.step()
+                    losses.append(float(loss.detach()))
+            weights = model.flat.data.clone()
+        torch.cuda.synchronize()
+        return losses, weights
+
+    le, we = run(False)
+    lg, wg = run(True)
+    assert all(abs(a - b) < 3e-2 * max(1.0, abs(a)) for a, b in zip(le, lg)), (le, lg)  # bf16 + atomics: not bit-exact
+    # SGD is linear in the gradients (Adam's sign-like update would amplify the atomics' summation-order noise): the weights
+    # after 8 steps must agree to bf16 gradient noise, and must have moved by far more than that
+    # yard-stick: two EAGER runs already differ (fp32 atomics in the weight-gradient kernels make the summation order, hence
+    # the bf16 roundings downstream, run-dependent); the graphed run must stay within a small multiple of that
+    _, we2 = run(False)
+    noise = float((we - we2).norm())
+    moved = float((we - wg).norm())
+    torch.manual_seed(5)
+    w_init = Model(ns).cuda().configure_optimizers().flat.data.clone()
+    travel = float((we - w_init).norm())
+    assert moved < max(3.0 * noise, 0.02 * travel) and moved < 0.25 * travel, (moved, noise, travel)

@@ -25,6 +25,7 @@ ap.add_argument("--size", type=int, default=1024)
 ap.add_argument("--deep_supervision", action="store_true")
 ap.add_argument("--attention", action="store_true")
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--graph", action="store_true", help="capture forward+backward in a CUDA graph")
 ap.add_argument("--gflop", type=float, default=0.0, help="fwd+bwd GFLOP per unit (SURVEY.md 8d) for the roofline fraction")
 a = ap.parse_args()
 a.gpus = 1
@@ -51,6 +52,10 @@ def step():
     return loss
 
 
+if a.graph:
+    from xview2_b200.graph import GraphedTrainStep
+    gstep = GraphedTrainStep(model, opt, batch)
+    step = lambda: gstep(batch)  # noqa: E731
 for _ in range(3):
     step()
 torch.cuda.synchronize()
@@ -64,6 +69,6 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 params = sum(p.numel() for p in model.parameters()) / 1e6
 frac = f", {a.gflop * a.batch / ms:.0f} TFLOP/s = {a.gflop * a.batch / ms / bench.measured_peaks()['tensor']:.3f} of the sustained bf16 peak" if a.gflop else ""
-print(f"{a.name}: {a.encoder} {a.type}/{a.dmg_model} ds={a.deep_supervision} attn={a.attention} batch {a.batch}: {ms:.1f} ms/step, "
+print(f"{a.name}{" [graph]" if a.graph else ""}: {a.encoder} {a.type}/{a.dmg_model} ds={a.deep_supervision} attn={a.attention} batch {a.batch}: {ms:.1f} ms/step, "
       f"{a.batch / ms * 1e3:.1f} {'pairs' if post else 'tiles'}/s, {(lib.launches() - n0) // a.steps} launches/step, {params:.1f} M params, "
       f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB, loss {float(loss):.4f}{frac}")

@@ -1,0 +1,65 @@
+"""CUDA-graph capture of the training step's device work.
+
+One training step is 500-3 800 kernel launches issued from Python (ctypes + autograd bookkeeping, ~35 us each): at small
+per-GPU batches (BASELINE config 4: 2 pairs) the launch rate, not the kernels, bounds the step.  ``GraphedTrainStep`` captures
+
+    zero_grad -> Model.training_step (tile normalise, U-Net forward, loss) -> backward
+
+once into a ``torch.cuda.CUDAGraph`` (all libxv2 launches go to torch's current stream, so they are recorded like any other
+kernel; TMA descriptors are encoded on the host at capture time and stay valid because the graph's private memory pool
+keeps every activation at a fixed address) and replays it per step.  The gradient all-reduce, the fused optimizer (whose
+learning rate / step count are host scalars that change every step) and the batched weight re-pack stay eager: 3 launches.
+
+    step = GraphedTrainStep(model, optimizer, batch)     # batch: dict of device tensors with the shapes of every later batch
+    loss = step(batch)                                   # device tensor, valid until the next call
+
+Stream rule (autograd): the gradient accumulators of the parameters belong to the stream on which the model FIRST ran.  If
+eager steps precede the capture they must have run on a non-default stream and that stream must be passed as ``stream=``
+(``Trainer.fit`` does this); capturing on a stream other than theirs would make the legacy stream depend on the capture.
+"""
+import torch
+
+from . import lib
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, batch, warmup=3, stream=None):
+        self.model, self.optimizer, self.flat = model, optimizer, model.flat
+        if self.flat is None:
+            raise lib.Xv2Error("configure_optimizers() must run before the step is captured (flat parameter buffer)")
+        self.static = {k: torch.empty_like(v).copy_(v) for k, v in batch.items()}
+        cur = torch.cuda.current_stream()
+        self.stream = stream if stream is not None else torch.cuda.Stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):  # warm-up on the capture stream: allocator, packed weights, accumulators settle
+            for _ in range(warmup):
+                self._forward_backward()
+                self._finish()
+        cur.wait_stream(self.stream)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        before = lib.launches()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self.loss = self._forward_backward()
+        self.launches_per_replay = lib.launches() - before
+
+    def _forward_backward(self):
+        self.optimizer.zero_grad()
+        loss = self.model.training_step(self.static, 0)
+        loss.backward()
+        return loss.detach()
+
+    def _finish(self):
+        n = self.flat.all_reduce_grads()
+        self.optimizer.grad_scale = 1.0 / n
+        self.optimizer.step()
+
+    def __call__(self, batch):
+        for k, dst in self.static.items():
+            src = batch[k]
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        lib.add_launches(self.launches_per_replay)
+        self._finish()
+        return self.loss

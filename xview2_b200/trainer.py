@@ -71,7 +71,8 @@ class ModelCheckpoint:
 class Trainer:
     def __init__(self, gpus=1, logger=False, precision=16, benchmark=True, deterministic=False, num_sanity_val_steps=0,
                  callbacks=None, max_epochs=1, min_epochs=1, sync_batchnorm=False, accelerator=None, default_root_dir=".",
-                 checkpoint_callback=None, resume_from_checkpoint=None, limit_train_batches=None, limit_val_batches=None):
+                 checkpoint_callback=None, resume_from_checkpoint=None, limit_train_batches=None, limit_val_batches=None,
+                 use_cuda_graph=False):
         self.gpus = max(1, int(gpus))
         self.precision = precision
         self.callbacks = callbacks or []
@@ -83,6 +84,7 @@ class Trainer:
         self.checkpoint_callback = checkpoint_callback
         self.resume_from_checkpoint = resume_from_checkpoint
         self.limit_train_batches, self.limit_val_batches = limit_train_batches, limit_val_batches
+        self.use_cuda_graph = use_cuda_graph  # opt-in: replay forward + backward from one CUDA graph (xview2_b200.graph)
         self.datamodule = None
         self.global_rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -136,17 +138,38 @@ class Trainer:
         ops.enable_wgrad_side_stream(True)  # step()/all_reduce_grads()/zero_grad() below are the sync points
         if resume is not None and resume.get("optimizer"):
             optimizer.load_state_dict(resume["optimizer"])
+        graphed = None
+        # all training work runs on one non-default stream, so that a CUDA-graph capture can share it with the eager steps
+        train_stream = torch.cuda.Stream() if self.use_cuda_graph else torch.cuda.current_stream()
+        train_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(train_stream):
+            self._fit_epochs(model, datamodule, train_loader, val_loader, optimizer, scheduler, flat, start_epoch, train_stream)
+        torch.cuda.current_stream().wait_stream(train_stream)
+        return model
+
+    def _fit_epochs(self, model, datamodule, train_loader, val_loader, optimizer, scheduler, flat, start_epoch, train_stream):
+        graphed = None
         for epoch in range(start_epoch, self.max_epochs):
             model.current_epoch = epoch
             model.train()
             if hasattr(train_loader, "set_epoch"):
                 train_loader.set_epoch(epoch)
             for i, batch in self._limited(train_loader, self.limit_train_batches):
-                optimizer.zero_grad()
-                loss = model.training_step(batch, i)
-                loss.backward()
-                optimizer.grad_scale = 1.0 / flat.all_reduce_grads()
-                optimizer.step()
+                if self.use_cuda_graph and graphed is None and self.global_step >= 1:
+                    try:  # static shapes (drop_last loader): after one eager step (caches warm) capture forward + backward once
+                        from .graph import GraphedTrainStep
+                        graphed = GraphedTrainStep(model, optimizer, batch, warmup=0, stream=train_stream)
+                    except Exception as exc:  # noqa: BLE001 -- capture is an optimisation; the eager step is always valid
+                        print(f"CUDA-graph capture unavailable ({type(exc).__name__}: {exc}); running eagerly", flush=True)
+                        self.use_cuda_graph = False
+                if graphed is not None:
+                    loss = graphed(batch)
+                else:
+                    optimizer.zero_grad()
+                    loss = model.training_step(batch, i)
+                    loss.backward()
+                    optimizer.grad_scale = 1.0 / flat.all_reduce_grads()
+                    optimizer.step()
                 if scheduler is not None:
                     scheduler.step()
                 self.global_step += 1
