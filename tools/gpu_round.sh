@@ -16,6 +16,10 @@ for s in $STAGES; do
     layers) timeout 600 python tools/layer_profile.py > gpurun_out/layers.txt 2> gpurun_out/layers.err; head -3 gpurun_out/layers.txt; tail -3 gpurun_out/layers.err ;;
     launches) timeout 1200 $NCU --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
         --log-file gpurun_out/launches.csv python tools/layer_profile.py --ncu > gpurun_out/launches.log 2>&1; wc -l gpurun_out/launches.csv ;;
+    launches_bench) timeout 1500 $NCU --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv \
+        --log-file gpurun_out/launches_bench.csv env XV2_NO_GRAPH=1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; wc -l gpurun_out/launches_bench.csv ;;
+    ncu_all) timeout 1500 $NCU --set full --clock-control none --import-source on --profile-from-start off \
+        -k regex:"conv_strip_kernel|conv_tc_kernel|wgrad_strip_kernel|wgrad_tc_kernel|bn_stream_kernel" -s 180 -c 14 -f -o gpurun_out/prof_all python tools/layer_profile.py --ncu > gpurun_out/ncu_all.log 2>&1; tail -2 gpurun_out/ncu_all.log ;;
     ncu_conv) timeout 1200 $NCU --set full --clock-control none --import-source on --profile-from-start off \
         -k regex:conv_tc_kernel -s 0 -c 4 -f -o gpurun_out/prof_conv python tools/layer_profile.py --ncu > gpurun_out/ncu_conv.log 2>&1; tail -3 gpurun_out/ncu_conv.log ;;
     ncu_strip) timeout 1200 $NCU --set full --clock-control none --import-source on --profile-from-start off \

@@ -201,6 +201,35 @@ def _wgrad_scope(direct, device, *tensors):
     return _OnSide(device, *tensors) if (direct and WGRAD_SIDE_STREAM and lib._profile is None) else _Inline()
 
 
+# Zero-initialised scratch (BN statistic accumulators, reduction buffers): one arena per device, cleared by ONE memset at the
+# start of a step (FlatParams.zero_grad) and bump-allocated, instead of ~200 torch.zeros launches per step.  Views are only
+# valid within the step that allocated them; outside a training loop (no zero_grad) the arena runs out and torch.zeros serves.
+_ZARENA_BYTES = 16 << 20
+_zarena = {}
+
+
+def new_step_scratch(device):
+    st = _zarena.get(device.index)
+    if st is None:
+        _zarena[device.index] = [torch.zeros(_ZARENA_BYTES, dtype=torch.uint8, device=device), 0]
+    else:
+        st[0].zero_()
+        st[1] = 0
+
+
+def zeros_scratch(shape, dtype, device):
+    st = _zarena.get(device.index)
+    n = 1
+    for d in (shape if isinstance(shape, (tuple, list)) else (shape,)):
+        n *= int(d)
+    nbytes = n * torch.empty(0, dtype=dtype).element_size()
+    if st is None or st[1] + nbytes > _ZARENA_BYTES:
+        return torch.zeros(shape, dtype=dtype, device=device)
+    off = st[1]
+    st[1] = (off + nbytes + 15) & ~15
+    return st[0][off:off + nbytes].view(dtype).view(shape)
+
+
 def _out_size(i, k, stride, pad, dil):
     return (i + 2 * pad - dil * (k - 1) - 1) // stride + 1
 
@@ -260,7 +289,7 @@ class _Conv2d(torch.autograd.Function):
             lib.note_work(2.0 * n * h * w * k * cg * r * s, 2.0 * n * h * w * (c0 + c1 + k) + 2.0 * k * cg * r * s,
                           f"fwd n{n} {h}x{w} c{c0}+{c1} k{k} {r}x{s} g{groups}")
             if want_stats:  # BN statistics fused into the conv epilogue (shapes served by the strip kernel)
-                stats = torch.zeros(2 * k, dtype=torch.float64, device=x.device)
+                stats = zeros_scratch(2 * k, torch.float64, x.device)
                 work = lib._work
                 rc = call("xv2_conv_tc", p, ptr(x), ptr(x2), ptr(wp), ptr(bias), ptr(out), ptr(stats), allow_unsupported=True)
                 if rc == 0:
@@ -453,7 +482,7 @@ class _BatchNormAct(torch.autograd.Function):
             if pixels <= 1:
                 raise ValueError("Expected more than 1 value per channel when training")  # torch's own BN check
             if stats is None:
-                stats = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+                stats = zeros_scratch(2 * c, torch.float64, dev)
                 call("xv2_bn_stats", ptr(x), pixels, c, dtype_code(x), ptr(stats))
             y = torch.empty_like(x)
             call("xv2_bn_train_apply", ptr(x), ptr(residual), ptr(y), pixels, c, dtype_code(x), ptr(stats), pixels, ptr(gamma),
@@ -478,7 +507,7 @@ class _BatchNormAct(torch.autograd.Function):
         pixels = n * h * w
         mean, invstd, scale, shift = coef[0], coef[1], coef[2], coef[3]
         dt = dtype_code(x)
-        red = torch.zeros(2 * c, dtype=torch.float64, device=x.device)
+        red = zeros_scratch(2 * c, torch.float64, x.device)
         call("xv2_bn_bwd_reduce", ptr(dy), ptr(x), ptr(residual), pixels, c, dt, ptr(scale), ptr(shift), ptr(mean),
              ptr(invstd), act, ptr(red))
         dx = torch.empty_like(x)
@@ -706,7 +735,7 @@ class _SplitAttention(torch.autograd.Function):
         c = c2 // 2
         inter = w1.shape[0]
         dev = x.device
-        datt = torch.zeros((n, c2), dtype=torch.float32, device=dev)
+        datt = zeros_scratch((n, c2), torch.float32, dev)
         call("xv2_splat_bwd_att", ptr(x), ptr(dout), ptr(datt), n, h * w, c, dtype_code(x))
         w2t = pack_weight(w2, 1, torch.float32)  # [inter][2c]
         w1t = pack_weight(w1, 1, torch.float32)  # [c][inter]

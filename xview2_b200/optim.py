@@ -56,6 +56,8 @@ class FlatParams:
     def zero_grad(self):
         ops.sync_side_streams()
         self.grad.zero_()
+        if self.grad.is_cuda:
+            ops.new_step_scratch(self.grad.device)  # the step's zero-initialised scratch arena: one memset
 
     def all_reduce_grads(self, group=None):
         """all-reduce(SUM) of the flat gradient buffer over the data-parallel ranks; returns the world size (the 1/N
