@@ -34,26 +34,32 @@ def _precision(v):
     return "bf16" if v == "bf16" else int(v)
 
 
+# The reference's 15 top-level flags (main.py:29-53): (flag, type, default, choices, help).  Names and defaults are the
+# contract; the help texts are ours.
+_BASE_FLAGS = (
+    ("exec_mode", str, "train", ["train", "eval"], "train a model, or evaluate a checkpoint on the hold-out split"),
+    ("data", str, "/data", None, "dataset root holding train/, test/ (validation) and holdout/ (test)"),
+    ("results", str, "/results", None, "output directory: checkpoints/, logs, probs/ and targets/"),
+    ("gpus", int, 1, None, "B200s to use; > 1 starts one process per GPU"),
+    ("num_workers", int, 8, None, "PNG decode threads per process"),
+    ("batch_size", int, 16, None, "tiles (or pre/post pairs) per GPU and training step"),
+    ("val_batch_size", int, 13, None, "tiles per GPU and evaluation step"),
+    ("precision", _precision, 16, [16, 32, "bf16"], "16 / bf16: bf16 tensor-core kernels; 32: fp32 parity kernels"),
+    ("epochs", int, 250, None, "number of training epochs"),
+    ("patience", int, 100, None, "epochs without an F1 improvement before training stops early"),
+    ("ckpt", str, None, None, "checkpoint to resume from (train) or to evaluate (eval)"),
+    ("logname", str, "logs", None, "basename of the JSON-lines log in --results"),
+    ("ckpt_pre", str, None, None, "localisation checkpoint whose encoder initialises the damage model (--type post)"),
+    ("type", str, None, ["pre", "post"], "pre: building localisation; post: damage assessment on pre/post pairs"),
+    ("seed", int, 1, None, "random seed"),
+)
+
+
 def build_parser():
     parser = ArgumentParser(formatter_class=ArgumentDefaultsHelpFormatter)
-    arg = parser.add_argument
-    arg("--exec_mode", type=str, choices=["train", "eval"], default="train", help="Execution mode of main script")
-    arg("--data", type=str, default="/data", help="Path to the data directory")
-    arg("--results", type=str, default="/results", help="Path to the results directory")
-    arg("--gpus", type=int, default=1, help="Number of gpus to use")
-    arg("--num_workers", type=int, default=8, help="Number of decode threads used for data loading")
-    arg("--batch_size", type=int, default=16, help="Training batch size")
-    arg("--val_batch_size", type=int, default=13, help="Evaluation batch size")
-    arg("--precision", type=_precision, default=16, choices=[16, 32, "bf16"], help="Numerical precision")
-    arg("--epochs", type=int, default=250, help="Max number of epochs")
-    arg("--patience", type=int, default=100, help="Early stopping patience")
-    arg("--ckpt", type=str, default=None, help="Path to pretrained checkpoint")
-    arg("--logname", type=str, default="logs", help="Name of logging file")
-    arg("--ckpt_pre", type=str, default=None,
-        help="Path to pretrained checkpoint of localization model used to initialize network for damage assesment")
-    arg("--type", type=str, choices=["pre", "post"],
-        help="Type of task to run; pre - localization, post - damage assesment")
-    arg("--seed", type=int, default=1)
+    for name, kind, default, choices, text in _BASE_FLAGS:
+        extra = {"choices": choices} if choices else {}
+        parser.add_argument(f"--{name}", type=kind, default=default, help=text, **extra)
     return Model.add_model_specific_args(parser)
 
 

@@ -233,37 +233,42 @@ class Model(nn.Module):
         }
         return {"optimizer": optimizer, "lr_scheduler": scheduler}
 
-    @staticmethod
-    def add_model_specific_args(parent_parser):
-        """The 21 model flags of plt.py:181-234 with the reference's defaults and choices."""
+    # The reference's 21 model flags (plt.py:185-233): names, defaults and choices are the contract, help texts are ours.
+    _VALUE_FLAGS = (
+        ("optimizer", str, "adamw", ["sgd", "adam", "adamw", "radam", "adabelief", "adabound", "adamp", "novograd"],
+         "optimizer; adamw / adam / sgd run as fused flat-buffer kernels"),
+        ("dmg_model", str, "siamese", ["siamese", "siameseEnc", "fused", "fusedEnc", "parallel", "parallelEnc", "diff", "cat"],
+         "how the pre and post images are combined for damage assessment"),
+        ("encoder", str, "resnest200", ["resnest50", "resnest101", "resnest200", "resnest269", "resnet50", "resnet101", "resnet152"],
+         "encoder of the U-Net"),
+        ("loss_str", str, "focal+dice", None, "'+'-joined loss terms out of dice, focal, ce, ohem (mse / coral: not accelerated)"),
+        ("warmup", int, 1, None, "Noam schedule: warm-up epochs"),
+        ("init_lr", float, 1e-4, None, "Noam schedule: learning rate at step 0"),
+        ("final_lr", float, 1e-4, None, "Noam schedule: learning rate at the last step"),
+        ("lr", float, 3e-4, None, "learning rate (the peak when the Noam schedule is on)"),
+        ("weight_decay", float, 0, None, "decoupled weight decay"),
+        ("momentum", float, 0.9, None, "SGD momentum"),
+        ("dilation", int, 1, [1, 2, 4], "2 / 4: replace the stride of the last one / two encoder stages by dilation"),
+    )
+    _SWITCHES = (
+        ("use_scheduler", "step the Noam learning-rate schedule"),
+        ("tta", "average the logits over the four flips at evaluation"),
+        ("ppm", "pyramid pooling module (not accelerated)"),
+        ("aspp", "atrous spatial pyramid pooling (not accelerated)"),
+        ("no_skip", "decoder without skip connections"),
+        ("deep_supervision", "auxiliary heads on the two coarser decoder stages"),
+        ("attention", "attention gates on the skip connections"),
+        ("autoaugment", "ImageNet auto-augment policy (not accelerated)"),
+        ("interpolate", "bilinear head on the encoder output instead of a decoder (not accelerated)"),
+        ("dec_interp", "bilinear up-sampling in the decoder (not accelerated)"),
+    )
+
+    @classmethod
+    def add_model_specific_args(cls, parent_parser):
         parser = ArgumentParser(parents=[parent_parser], add_help=False)
-        arg = parser.add_argument
-        arg("--optimizer", type=str, default="adamw",
-            choices=["sgd", "adam", "adamw", "radam", "adabelief", "adabound", "adamp", "novograd"])
-        arg("--dmg_model", type=str, default="siamese",
-            choices=["siamese", "siameseEnc", "fused", "fusedEnc", "parallel", "parallelEnc", "diff", "cat"],
-            help="U-Net variant for damage assessment task")
-        arg("--encoder", type=str, default="resnest200",
-            choices=["resnest50", "resnest101", "resnest200", "resnest269", "resnet50", "resnet101", "resnet152"],
-            help="U-Net encoder")
-        arg("--loss_str", type=str, default="focal+dice",
-            help="Combination of: dice, focal, ce, ohem, mse, coral, e.g focal+dice creates the loss function as sum of focal and dice")
-        arg("--use_scheduler", action="store_true", help="Enable Noam learning rate scheduler")
-        arg("--warmup", type=int, default=1, help="Warmup epochs for Noam learning rate scheduler")
-        arg("--init_lr", type=float, default=1e-4, help="Initial learning rate for Noam scheduler")
-        arg("--final_lr", type=float, default=1e-4, help="Final learning rate for Noam scheduler")
-        arg("--lr", type=float, default=3e-4, help="Learning rate, or a target learning rate for Noam scheduler")
-        arg("--weight_decay", type=float, default=0, help="Weight decay (L2 penalty)")
-        arg("--momentum", type=float, default=0.9, help="Momentum for SGD optimizer")
-        arg("--dilation", type=int, choices=[1, 2, 4], default=1,
-            help="Dilation rate for a encoder, e.g dilation=2 uses dilation instead of stride in the last encoder block")
-        arg("--tta", action="store_true", help="Enable test time augmentation")
-        arg("--ppm", action="store_true", help="Use pyramid pooling module")
-        arg("--aspp", action="store_true", help="Use atrous spatial pyramid pooling")
-        arg("--no_skip", action="store_true", help="Disable skip connections in UNet")
-        arg("--deep_supervision", action="store_true", help="Enable deep supervision")
-        arg("--attention", action="store_true", help="Enable attention module at the decoder")
-        arg("--autoaugment", action="store_true", help="Use imageNet autoaugment pipeline")
-        arg("--interpolate", action="store_true", help="Interpolate feature map from encoder without a decoder")
-        arg("--dec_interp", action="store_true", help="Use interpolation instead of transposed convolution in a decoder")
+        for name, kind, default, choices, text in cls._VALUE_FLAGS:
+            extra = {"choices": choices} if choices else {}
+            parser.add_argument(f"--{name}", type=kind, default=default, help=text, **extra)
+        for name, text in cls._SWITCHES:
+            parser.add_argument(f"--{name}", action="store_true", help=text)
         return parser

@@ -1,44 +1,49 @@
-"""Noam learning-rate schedule with the reference's constructor (/root/reference/utils/scheduler.py:6-59): linear warm-up
-from init_lr to max_lr over warmup_epochs * steps_per_epoch steps, then exponential decay to final_lr at total steps.
-Host-side scalar arithmetic; stepped once per optimizer step."""
-import numpy as np
+"""Noam learning-rate schedule behind the reference's ``NoamLR`` constructor (/root/reference/utils/scheduler.py:6-59).
+
+The schedule is a closed form in the step index t (stepped once per optimizer step, plt.py:163-178):
+
+    t <= W      : lr = init + t * (peak - init) / W                   linear warm-up over W = warmup_epochs * steps_per_epoch
+    W < t <= T  : lr = peak * (final / peak) ** ((t - W) / (T - W))   exponential decay down to `final` at T = total steps
+    t > T       : lr = final
+
+times a per-group coefficient (``fine_tune_coff`` for group ``fine_tune_param_idx``, 1 elsewhere).  Host-side scalar math.
+"""
+
+
+def noam_value(t, warmup_steps, total_steps, init_lr, peak_lr, final_lr):
+    if t <= warmup_steps:
+        return init_lr + t * (peak_lr - init_lr) / max(warmup_steps, 1)
+    if t <= total_steps:
+        return peak_lr * (final_lr / peak_lr) ** ((t - warmup_steps) / max(total_steps - warmup_steps, 1))
+    return final_lr
 
 
 class NoamLR:
     def __init__(self, optimizer, warmup_epochs, total_epochs, steps_per_epoch, init_lr, max_lr, final_lr,
                  fine_tune_coff=1.0, fine_tune_param_idx=0):
         self.optimizer = optimizer
-        self.num_lrs = len(optimizer.param_groups)
-        n = self.num_lrs
+        groups = optimizer.param_groups
         self.steps_per_epoch = steps_per_epoch
-        self.init_lr = np.array([init_lr] * n, dtype=np.float64)
-        self.max_lr = np.array([max_lr] * n, dtype=np.float64)
-        self.final_lr = np.array([final_lr] * n, dtype=np.float64)
-        self.lr_coff = np.array([1.0] * n)
-        self.lr_coff[fine_tune_param_idx] = fine_tune_coff
+        self.warmup_steps = int(warmup_epochs * steps_per_epoch)
+        self.total_steps = total_epochs * steps_per_epoch
+        self.shape = (float(init_lr), float(max_lr), float(final_lr))
+        self.coefficients = [fine_tune_coff if g == fine_tune_param_idx else 1.0 for g in range(len(groups))]
         self.current_step = 0
-        self.lr = [init_lr] * n
-        self.warmup_steps = (np.array([warmup_epochs] * n) * steps_per_epoch).astype(int)
-        self.total_steps = np.array([total_epochs] * n) * steps_per_epoch
-        self.linear_increment = (self.max_lr - self.init_lr) / np.maximum(self.warmup_steps, 1)
-        self.exponential_gamma = (self.final_lr / self.max_lr) ** (1 / np.maximum(self.total_steps - self.warmup_steps, 1))
-        for i, group in enumerate(optimizer.param_groups):
-            group["lr"] = self.lr[i]
+        self.lr = [init_lr for _ in groups]
+        self._publish()
+
+    def _publish(self):
+        for group, lr in zip(self.optimizer.param_groups, self.lr):
+            group["lr"] = lr
 
     def get_lr(self):
         return list(self.lr)
 
     def step(self, current_step=None):
-        self.current_step = current_step if current_step is not None else self.current_step + 1
-        for i in range(self.num_lrs):
-            if self.current_step <= self.warmup_steps[i]:
-                lr = self.init_lr[i] + self.current_step * self.linear_increment[i]
-            elif self.current_step <= self.total_steps[i]:
-                lr = self.max_lr[i] * (self.exponential_gamma[i] ** (self.current_step - self.warmup_steps[i]))
-            else:
-                lr = self.final_lr[i]
-            self.lr[i] = float(lr * self.lr_coff[i])
-            self.optimizer.param_groups[i]["lr"] = self.lr[i]
+        self.current_step = self.current_step + 1 if current_step is None else current_step
+        base = noam_value(self.current_step, self.warmup_steps, self.total_steps, *self.shape)
+        self.lr = [float(base * k) for k in self.coefficients]
+        self._publish()
 
     def state_dict(self):
         return {"current_step": self.current_step, "lr": list(self.lr)}
@@ -46,5 +51,4 @@ class NoamLR:
     def load_state_dict(self, sd):
         self.current_step = sd["current_step"]
         self.lr = list(sd["lr"])
-        for i, group in enumerate(self.optimizer.param_groups):
-            group["lr"] = self.lr[i]
+        self._publish()
