@@ -226,3 +226,33 @@ def test_flat_gradient_allreduce_gloo_world2():
         same, n, g0, alias = out[rank]
         assert same and n == 2 and alias
         assert g0 == float(sum(range(10)))  # SUM over ranks of disjoint tile shards = sum over all tiles
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host steps of utils/post_process.py (connected-component vote, dilation) against the reference's own formulation
+# ---------------------------------------------------------------------------------------------------------------
+def test_majority_vote_and_dilation_match_reference_formulation():
+    from scipy.ndimage import label
+
+    from xview2_b200.utils.post_process import dilate, majority_vote
+
+    rng = np.random.default_rng(4)
+    cells = rng.integers(0, 5, (24, 24))
+    cells[rng.random((24, 24)) < 0.45] = 0
+    post = np.kron(cells, np.ones((8, 8), dtype=np.int64)).astype(np.uint8)
+    noise = rng.random(post.shape) < 0.2
+    post[noise & (post > 0)] = rng.integers(1, 5, int((noise & (post > 0)).sum()))
+    ref = post.copy()
+    components, n = label(ref > 0)  # the reference's loop, post_process.py:39-43
+    for b in range(1, n + 1):
+        labels, counts = np.unique(ref[components == b], return_counts=True)
+        ref[components == b] = labels[np.argmax(counts)]
+    assert n > 5 and np.array_equal(majority_vote(post), ref)
+    assert np.array_equal(majority_vote(np.zeros((8, 8), np.uint8)), np.zeros((8, 8), np.uint8))
+    # square grey dilation == running maximum over the k x k window clipped at the border (skimage dilation(img, square(k)))
+    for k in (3, 5):
+        out = dilate(post, k)
+        pad = k // 2
+        padded = np.pad(post, pad, constant_values=0)
+        want = np.max([padded[i:i + post.shape[0], j:j + post.shape[1]] for i in range(k) for j in range(k)], axis=0)
+        assert np.array_equal(out, want)

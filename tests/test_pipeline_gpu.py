@@ -105,3 +105,37 @@ def test_fit_checkpoint_test_postprocess(tmp_path, monkeypatch, task):
     pre_ref = (p0 > 0.3) | ((p0 > 0.1) & (post_ref > 1))
     assert np.array_equal(pre_map.cpu().numpy().astype(bool), pre_ref)
     assert np.array_equal(post_map.cpu().numpy(), (post_ref * pre_ref).astype(np.uint8))
+
+
+def test_post_process_cli(tmp_path):
+    """xview2_b200.utils.post_process (reference utils/post_process.py): probs/*.npy -> predictions/*.png, against a numpy
+    restatement of post_process.py:27-47 including the connected-component vote and the dilation."""
+    from PIL import Image
+    from scipy.ndimage import grey_dilation, label
+
+    from xview2_b200.utils import post_process as pp
+
+    rng = np.random.default_rng(11)
+    os.makedirs(tmp_path / "probs")
+    cases = []
+    for i in range(2):
+        coarse = rng.random((64, 64)).astype(np.float32)
+        loc = np.kron(coarse, np.ones((16, 16), np.float32)) * 0.9 + rng.random((1024, 1024)).astype(np.float32) * 0.1
+        dmg = rng.random((4, 1024, 1024)).astype(np.float32)
+        dmg /= dmg.sum(0, keepdims=True)
+        np.save(tmp_path / "probs" / f"test_localization_{i:05d}.npy", loc)
+        np.save(tmp_path / "probs" / f"test_damage_{i:05d}.npy", dmg)
+        cases.append((loc, dmg))
+    assert pp.main(["--results", str(tmp_path), "--components", "--dilate", "--dilation_rate", "3"]) == 2
+    for i, (loc, dmg) in enumerate(cases):
+        post = np.argmax(dmg, axis=0) + 1
+        pre = ((loc > 0.3) | ((loc > 0.1) & (post > 1))).astype(np.int64)
+        post = post * pre
+        components, n = label(post > 0)
+        for b in range(1, n + 1):
+            labels, counts = np.unique(post[components == b], return_counts=True)
+            post[components == b] = labels[np.argmax(counts)]
+        pre, post = grey_dilation(pre, size=(3, 3)), grey_dilation(post, size=(3, 3))
+        got_pre = np.array(Image.open(tmp_path / "predictions" / f"test_localization_{i:05d}_prediction.png"))
+        got_post = np.array(Image.open(tmp_path / "predictions" / f"test_damage_{i:05d}_prediction.png"))
+        assert np.array_equal(got_pre, pre.astype(np.uint8)) and np.array_equal(got_post, post.astype(np.uint8))
