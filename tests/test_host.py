@@ -256,3 +256,30 @@ def test_majority_vote_and_dilation_match_reference_formulation():
         padded = np.pad(post, pad, constant_values=0)
         want = np.max([padded[i:i + post.shape[0], j:j + post.shape[1]] for i in range(k) for j in range(k)], axis=0)
         assert np.array_equal(out, want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# drop-in contract: state_dict keys and shapes of EVERY model variant == the reference's own modules
+# (tests/golden/state_keys.json, written by tools/make_state_keys.py from /root/reference/model/unet.py)
+# ---------------------------------------------------------------------------------------------------------------
+def _state_key_cases():
+    import json
+
+    with open(os.path.join(ROOT, "tests", "golden", "state_keys.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", sorted(_state_key_cases()))
+def test_state_dict_keys_match_reference(name):
+    from xview2_b200.model.unet import UNetLoc, get_dmg_unet
+
+    case = _state_key_cases()[name]
+    ns = argparse.Namespace(**case["args"])
+    model = UNetLoc(ns) if ns.type == "pre" else get_dmg_unet(ns)
+    ours = {k: list(v.shape) for k, v in model.state_dict().items()}
+    ref = case["keys"]
+    missing = sorted(set(ref) - set(ours))
+    extra = sorted(set(ours) - set(ref))
+    assert not missing and not extra, (missing[:5], extra[:5])
+    wrong = [(k, ours[k], ref[k]) for k in ref if ours[k] != ref[k]]
+    assert not wrong, wrong[:5]
