@@ -10,6 +10,9 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from oracle import functional as OF  # noqa: E402
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -178,12 +181,139 @@ def test_noam_lr_warmup_then_decay():
         param_groups = [{"lr": 0.0}]
 
     sch = NoamLR(Opt(), warmup_epochs=1, total_epochs=3, steps_per_epoch=10, init_lr=1e-4, max_lr=1e-3, final_lr=1e-5)
-    lrs = []
+    # torch's _LRScheduler.__init__ (the reference's base class) steps once at construction: the first batch trains at step 1
+    assert sch.current_step == 1 and abs(Opt.param_groups[0]["lr"] - (1e-4 + 9e-5)) < 1e-12
+    lrs = [Opt.param_groups[0]["lr"]]
     for _ in range(30):
         sch.step()
         lrs.append(Opt.param_groups[0]["lr"])
     assert abs(lrs[9] - 1e-3) < 1e-9 and all(b > a for a, b in zip(lrs[:9], lrs[1:10]))
-    assert all(b < a for a, b in zip(lrs[10:], lrs[11:])) and abs(lrs[-1] - 1e-5) < 1e-8
+    assert all(b < a for a, b in zip(lrs[10:29], lrs[11:30])) and abs(lrs[-1] - 1e-5) < 1e-8
+    for t, lr in enumerate(lrs, start=1):
+        assert abs(lr - OF.noam_lr(t, 10, 30, 1e-4, 1e-3, 1e-5)) < 1e-12
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/utils/scheduler.py"), reason="reference tree not present")
+def test_noam_lr_equals_reference_class_step_for_step():
+    import importlib.util
+
+    from xview2_b200.utils.scheduler import NoamLR
+
+    spec = importlib.util.spec_from_file_location("ref_scheduler", "/root/reference/utils/scheduler.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    kw = dict(warmup_epochs=2, total_epochs=5, steps_per_epoch=7, init_lr=1e-4, max_lr=3e-4, final_lr=2e-5)
+    p = torch.nn.Parameter(torch.zeros(1))
+    ref_opt = torch.optim.SGD([p], lr=1.0)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_sch = ref.NoamLR(optimizer=ref_opt, **kw)
+
+        class Opt:
+            param_groups = [{"lr": 0.0}]
+
+        ours = NoamLR(Opt(), **kw)
+        for _ in range(40):
+            assert abs(Opt.param_groups[0]["lr"] - ref_opt.param_groups[0]["lr"]) < 1e-12
+            ref_sch.step()
+            ours.step()
+
+
+def test_noam_steps_per_epoch_is_per_rank_once(monkeypatch):
+    """TileLoader.__len__ is already per-rank; configure_optimizers must not divide by --gpus again."""
+    from xview2_b200.model import plt as xplt
+
+    class FakeFlat:
+        params = []
+
+    class FakeModel:
+        args = argparse.Namespace(optimizer="adamw", weight_decay=0.0, use_scheduler=True, warmup=1, epochs=4, gpus=4,
+                                  init_lr=1e-4, final_lr=1e-5, lr=3e-4, momentum=0.9)
+        lr = 3e-4
+        flat = FakeFlat()
+
+        def train_dataloader(self):
+            return range(25)  # 25 batches on THIS rank
+
+    made = {}
+
+    class FakeOpt:
+        def __init__(self, flat, **kw):
+            self.param_groups = [{"lr": kw["lr"]}]
+
+    monkeypatch.setattr(xplt, "FusedAdamW", FakeOpt)
+    conf = xplt.Model.configure_optimizers(FakeModel())
+    sch = conf["lr_scheduler"]["scheduler"]
+    assert sch.steps_per_epoch == 25 and sch.warmup_steps == 25 and sch.total_steps == 100
+
+
+def test_reference_checkpoint_with_metric_states_loads_strictly():
+    """pytorch_lightning 1.0 Metric states are persistent: reference checkpoints carry f1_score.tp/fp/fn."""
+    from xview2_b200.model.plt import Model
+
+    ns = argparse.Namespace(ppm=False, aspp=False, dilation=1, no_skip=False, interpolate=False, attention=False,
+                            dec_interp=False, deep_supervision=False, loss_str="focal+dice", encoder="resnet50",
+                            dmg_model="siamese", type="post", tta=False, precision="bf16", lr=3e-4, results=None, logname="t")
+    m = Model(ns)
+    ck = m.checkpoint()
+    assert {"f1_score.tp", "f1_score.fp", "f1_score.fn"} <= set(ck["state_dict"])
+    sd = dict(ck["state_dict"])
+    sd["f1_score.tp"] = torch.tensor([1.0, 2.0, 3.0, 4.0])
+    sd["f1_score.fp"] = torch.tensor([5.0, 6.0, 7.0, 8.0])
+    sd["f1_score.fn"] = torch.zeros(4)
+    m2 = Model(ns).load_reference_state_dict(sd)
+    assert m2.f1_score.tp.tolist() == [1.0, 2.0, 3.0, 4.0] and m2.f1_score.fp.tolist() == [5.0, 6.0, 7.0, 8.0]
+    with pytest.raises(RuntimeError):  # still strict for everything else
+        m2.load_reference_state_dict({**sd, "model.bogus": torch.zeros(1)})
+
+
+def test_checkpoint_callback_saves_scheduler_and_global_step(tmp_path):
+    from xview2_b200.trainer import ModelCheckpoint
+    from xview2_b200.utils.scheduler import NoamLR
+
+    class Opt:
+        param_groups = [{"lr": 0.0}]
+
+        def state_dict(self):
+            return {"step": 3}
+
+    class FakeModel:
+        logged = {"f1_score": torch.tensor(0.5)}
+        current_epoch = 2
+
+        def checkpoint(self):
+            return {"state_dict": {}, "hyper_parameters": {}, "epoch": 2}
+
+    class FakeTrainer:
+        global_rank = 0
+        default_root_dir = str(tmp_path)
+        global_step = 77
+        scheduler = NoamLR(Opt(), 1, 3, 10, 1e-4, 1e-3, 1e-5)
+
+    FakeTrainer.scheduler.step(33)
+    cb = ModelCheckpoint(dirpath=str(tmp_path))
+    cb.on_epoch_end(FakeTrainer(), FakeModel(), Opt())
+    ck = torch.load(os.path.join(str(tmp_path), "last.ckpt"), weights_only=False)
+    assert ck["global_step"] == 77 and ck["lr_schedulers"][0]["current_step"] == 33
+    fresh = NoamLR(Opt(), 1, 3, 10, 1e-4, 1e-3, 1e-5)
+    fresh.load_state_dict(ck["lr_schedulers"][0])
+    assert fresh.current_step == 33 and abs(Opt.param_groups[0]["lr"] - FakeTrainer.scheduler.lr[0]) < 1e-15
+
+
+def test_intensity_augmentations_draw_per_image():
+    """intensity_aug (pytorch_loader.py:45-51) applies GaussNoise / RandomBrightnessContrast once per 3-channel image."""
+    import random
+
+    from xview2_b200.data_loading.pytorch_loader import TrainAugment
+
+    img = np.full((32, 32, 6), 100, np.uint8)
+    differ = 0
+    for seed in range(200):
+        out = TrainAugment._brightness_contrast(random.Random(seed), img)
+        a, b = out[:, :, :3], out[:, :, 3:]
+        differ += int(a[0, 0, 0] != b[0, 0, 0])
+    assert differ > 20  # with one shared draw the two halves would always be equal
 
 
 # ---------------------------------------------------------------------------------------------------------------

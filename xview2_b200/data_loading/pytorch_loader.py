@@ -95,24 +95,32 @@ class TrainAugment:
 
     @staticmethod
     def _noise(rng, nprng, img):
-        if rng.random() >= 0.1:
-            return img
-        sigma = rng.uniform(10.0, 50.0) ** 0.5
+        """A.GaussNoise(p=0.1): intensity_aug (pytorch_loader.py:45-51) calls the transform once PER IMAGE, so the pre and the
+        post tile each get their own probability draw, variance and noise field."""
         out = []
-        for i in range(0, img.shape[2], 3):  # the reference draws a separate noise field per image (intensity_aug, :45-51)
-            g = nprng.normal(0.0, sigma, img[:, :, i:i + 3].shape)
-            out.append(np.clip(img[:, :, i:i + 3].astype(np.float32) + g, 0, 255).astype(np.uint8))
-        return np.concatenate(out, 2)
+        for i in range(0, img.shape[2], 3):
+            part = img[:, :, i:i + 3]
+            if rng.random() < 0.1:
+                sigma = rng.uniform(10.0, 50.0) ** 0.5
+                g = nprng.normal(0.0, sigma, part.shape)
+                part = np.clip(part.astype(np.float32) + g, 0, 255).astype(np.uint8)
+            out.append(part)
+        return out[0] if len(out) == 1 else np.concatenate(out, 2)
 
     @staticmethod
     def _brightness_contrast(rng, img):
-        if rng.random() >= 0.2:
-            return img
-        alpha, beta = 1.0 + rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2)
-        lut = np.arange(0, 256, dtype=np.float32) * alpha
-        if beta != 0:
-            lut += beta * 255.0
-        return np.clip(lut, 0, 255).astype(np.uint8)[img]
+        """A.RandomBrightnessContrast(p=0.2), likewise one independent draw (p, alpha, beta) per 3-channel image."""
+        out = []
+        for i in range(0, img.shape[2], 3):
+            part = img[:, :, i:i + 3]
+            if rng.random() < 0.2:
+                alpha, beta = 1.0 + rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2)
+                lut = np.arange(0, 256, dtype=np.float32) * alpha
+                if beta != 0:
+                    lut += beta * 255.0
+                part = np.clip(lut, 0, 255).astype(np.uint8)[part]
+            out.append(part)
+        return out[0] if len(out) == 1 else np.concatenate(out, 2)
 
     def __call__(self, rng, nprng, img, lbl):
         img, lbl = self._zoom(rng, img, lbl)

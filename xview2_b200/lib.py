@@ -89,6 +89,7 @@ _lib = None
 _launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
 _profile = None  # when a list: (name, start_event, end_event, flops, bytes) per call -- bench.py's roofline pass
 _work = (0.0, 0.0, "")  # algorithmic (flops, bytes, tag) of the NEXT call, declared by ops.* through note_work()
+_scope = ""  # profiling scope (e.g. "fwd:enc_l3") attached to every recorded call; set by scope_hooks() / set_scope()
 
 
 class Xv2Error(RuntimeError):
@@ -155,16 +156,52 @@ def profile_start():
     _profile = []
 
 
-def profile_stop(per_call=False):
+def set_scope(name):
+    """Names the part of the step the following calls belong to (only read while profiling)."""
+    global _scope
+    _scope = name
+
+
+def scope_hooks(named_modules, prefix="fwd:"):
+    """Registers forward pre/post hooks that set the profiling scope to ``prefix + name`` while each module runs.
+    Returns the hook handles (call .remove() on each when done)."""
+    handles = []
+    for name, mod in named_modules:
+        def pre(_m, _i, name=name):
+            set_scope(prefix + name)
+
+        def post(_m, _i, _o):
+            set_scope(prefix + "other")
+
+        handles.append(mod.register_forward_pre_hook(pre))
+        handles.append(mod.register_forward_hook(post))
+    return handles
+
+
+def profile_by_scope(rows):
+    """{scope: {"ms", "flops", "bytes", "calls"}} from profile_stop(per_call=True, with_scope=True) rows."""
+    out = {}
+    for name, tag, ms, fl, by, scope in rows:
+        d = out.setdefault(scope, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["calls"] += 1
+        d["ms"] += ms
+        d["flops"] += fl
+        d["bytes"] += by
+    return out
+
+
+def profile_stop(per_call=False, with_scope=False):
     """Returns {entry point: {"calls", "ms", "flops", "bytes"}} measured with CUDA events on the launching stream
     (per_call=True: the raw list of (entry point, tag, ms, flops, bytes) instead)."""
     global _profile
     rec, _profile = _profile, None
     torch.cuda.synchronize()
+    if per_call and with_scope:
+        return [(name, tag, e0.elapsed_time(e1), fl, by, sc) for name, e0, e1, fl, by, tag, sc in rec or []]
     if per_call:
-        return [(name, tag, e0.elapsed_time(e1), fl, by) for name, e0, e1, fl, by, tag in rec or []]
+        return [(name, tag, e0.elapsed_time(e1), fl, by) for name, e0, e1, fl, by, tag, _sc in rec or []]
     out = {}
-    for name, e0, e1, fl, by, _tag in rec or []:
+    for name, e0, e1, fl, by, _tag, _sc in rec or []:
         d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
         d["calls"] += 1
         d["ms"] += e0.elapsed_time(e1)
@@ -183,7 +220,7 @@ def call(name, *args, allow_unsupported=False):
         rc = getattr(lib, name)(*args, stream_ptr())
         e1.record()
         if rc == 0:
-            _profile.append((name, e0, e1, _work[0], _work[1], _work[2]))
+            _profile.append((name, e0, e1, _work[0], _work[1], _work[2], _scope))
         _work = (0.0, 0.0, "")
     else:
         rc = getattr(lib, name)(*args, stream_ptr())

@@ -101,12 +101,24 @@ class Model(nn.Module):
         """main.py:74.  Reads a Lightning-style checkpoint dict: {"state_dict", "hyper_parameters": {"args": ...}}."""
         ckpt = torch.load(path, map_location=map_location, weights_only=False)
         model = cls(ckpt["hyper_parameters"]["args"])
-        model.load_state_dict(ckpt["state_dict"], strict=True)
+        model.load_reference_state_dict(ckpt["state_dict"])
         return model
 
+    def load_reference_state_dict(self, state_dict):
+        """Strict load of a checkpoint written by the reference or by this package.  pytorch_lightning 1.0 Metric states are
+        persistent, so reference checkpoints carry ``f1_score.tp / fp / fn`` (utils/f1.py:24-26); they are absorbed into the
+        device counters of xview2_b200.utils.f1.F1 instead of tripping the strict key check."""
+        sd = dict(state_dict)
+        metric = {k[len("f1_score."):]: sd.pop(k) for k in list(sd) if k.startswith("f1_score.")}
+        self.load_state_dict(sd, strict=True)
+        if all(k in metric for k in ("tp", "fp", "fn")):
+            self.f1_score.load_counts(metric["tp"], metric["fp"], metric["fn"])
+        return self
+
     def checkpoint(self):
-        return {"state_dict": {k: v.detach().cpu().clone() for k, v in self.state_dict().items()},
-                "hyper_parameters": self.hparams, "epoch": self.current_epoch}
+        sd = {k: v.detach().cpu().clone() for k, v in self.state_dict().items()}
+        sd.update({f"f1_score.{k}": getattr(self.f1_score, k).detach().cpu().clone() for k in ("tp", "fp", "fn")})  # PL Metric states
+        return {"state_dict": sd, "hyper_parameters": self.hparams, "epoch": self.current_epoch}
 
     # -- hooks (plt.py:42-67) -----------------------------------------------------------------------------------
     @staticmethod
@@ -226,7 +238,9 @@ class Model(nn.Module):
             return optimizer
         scheduler = {
             "scheduler": NoamLR(optimizer=optimizer, warmup_epochs=self.args.warmup, total_epochs=self.args.epochs,
-                                steps_per_epoch=len(self.train_dataloader()) // max(1, self.args.gpus),
+                                # plt.py:170 divides an UNSHARDED DataLoader length by args.gpus; TileLoader.__len__ is already
+                                # the per-rank batch count (shard_indices uses WORLD_SIZE), so it is used as is
+                                steps_per_epoch=len(self.train_dataloader()),
                                 init_lr=self.args.init_lr, max_lr=self.args.lr, final_lr=self.args.final_lr),
             "interval": "step",
             "frequency": 1,

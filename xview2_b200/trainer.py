@@ -56,6 +56,9 @@ class ModelCheckpoint:
         os.makedirs(d, exist_ok=True)
         ckpt = model.checkpoint()
         ckpt["optimizer"] = optimizer.state_dict() if optimizer is not None else None
+        ckpt["global_step"] = trainer.global_step
+        sched = getattr(trainer, "scheduler", None)
+        ckpt["lr_schedulers"] = [sched.state_dict()] if sched is not None else []  # PL's checkpoint key
         if self.save_last:
             torch.save(ckpt, os.path.join(d, "last.ckpt"))
         if self.monitor in model.logged:
@@ -80,6 +83,11 @@ class Trainer:
         # main.py:106 passes sync_batchnorm=gpus>1; north_star keeps ONE collective (the gradient all-reduce), so BN
         # statistics are rank-local here and the flag is accepted for signature parity only.
         self.sync_batchnorm = False
+        if sync_batchnorm:
+            import warnings
+            warnings.warn("sync_batchnorm=True is accepted for signature parity but BatchNorm statistics stay rank-local here "
+                          "(the gradient all-reduce is the only collective of this path); at very small per-GPU batches "
+                          "(e.g. 2 pairs) this differs from the reference's SyncBatchNorm run", stacklevel=2)
         self.default_root_dir = default_root_dir
         self.checkpoint_callback = checkpoint_callback
         self.resume_from_checkpoint = resume_from_checkpoint
@@ -90,6 +98,7 @@ class Trainer:
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
         self.global_step = 0
+        self.scheduler = None
 
     # -- process-per-GPU launch ----------------------------------------------------------------------------------
     def _maybe_spawn(self):
@@ -126,7 +135,7 @@ class Trainer:
         resume = None
         if self.resume_from_checkpoint and os.path.exists(self.resume_from_checkpoint):
             resume = torch.load(self.resume_from_checkpoint, map_location="cpu", weights_only=False)
-            model.load_state_dict(resume["state_dict"], strict=True)
+            model.load_reference_state_dict(resume["state_dict"])
             start_epoch = int(resume.get("epoch", -1)) + 1
         train_loader = datamodule.train_dataloader()
         val_loader = datamodule.val_dataloader()
@@ -136,8 +145,18 @@ class Trainer:
         flat.broadcast_params(0)
         from . import ops
         ops.enable_wgrad_side_stream(True)  # step()/all_reduce_grads()/zero_grad() below are the sync points
+        self.scheduler = scheduler
         if resume is not None and resume.get("optimizer"):
             optimizer.load_state_dict(resume["optimizer"])
+        if resume is not None:
+            # PL restores global_step and the lr_schedulers states; without them the Noam warm-up would be replayed
+            self.global_step = int(resume.get("global_step", start_epoch * max(1, len(train_loader))))
+            if scheduler is not None:
+                states = resume.get("lr_schedulers") or []
+                if states:
+                    scheduler.load_state_dict(states[0])
+                else:  # checkpoint without scheduler state: re-derive the position from the step count
+                    scheduler.step(self.global_step + 1)
         graphed = None
         # all training work runs on one non-default stream, so that a CUDA-graph capture can share it with the eager steps
         train_stream = torch.cuda.Stream() if self.use_cuda_graph else torch.cuda.current_stream()

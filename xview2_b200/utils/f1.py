@@ -47,10 +47,19 @@ class F1:
             return torch.zeros(k)
         return self.counters[i * k:(i + 1) * k].float()
 
+    def load_counts(self, tp, fp, fn):
+        """Restores the tp / fp / fn states of a checkpoint (pytorch_lightning Metric states are persistent)."""
+        c = torch.cat([torch.as_tensor(t).reshape(-1).to(torch.int64) for t in (tp, fp, fn)])
+        if c.numel() != 3 * (self.n_class - 1):
+            raise ValueError(f"F1 state of {c.numel()} counters does not fit n_class={self.n_class}")
+        self.counters = c if self.counters is None else c.to(self.counters.device)
+
     # -- Metric API -------------------------------------------------------------------------------------------
     def update(self, preds, targets, pred_map=None):
         if self.counters is None:
             self.counters = torch.zeros(3 * (self.n_class - 1), dtype=torch.int64, device=preds.device)
+        elif self.counters.device != preds.device:
+            self.counters = self.counters.to(preds.device)
         ops.f1_update(preds, targets, self.n_class, self.counters, pred_map)
 
     def __call__(self, preds, targets):

@@ -31,6 +31,9 @@ class NoamLR:
         self.current_step = 0
         self.lr = [init_lr for _ in groups]
         self._publish()
+        # torch's _LRScheduler.__init__ (the reference's base class, scheduler.py:41) calls self.step() once at construction,
+        # so the reference trains its first batch at the step-1 learning rate and stays one step ahead throughout
+        self.step()
 
     def _publish(self):
         for group, lr in zip(self.optimizer.param_groups, self.lr):
