@@ -272,6 +272,35 @@ int xv2_post_process_probs(const float* loc, const float* dmg, int64_t pixels, u
  * ncls 2: out[n][hw] = sigmoid(logit[..,1]);  ncls 4: out[n][4][hw] = softmax (planar). */
 int xv2_save_probs(const float* logits, int32_t n, int64_t hw, int32_t ncls, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Optional model parts: pyramid pooling, bilinear decoders / heads, ordinal damage heads.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* nn.AdaptiveAvgPool2d(bins) of PPM (layers.py:12-21): y[n][bins][bins][c]; bin i covers [floor(i L/bins), ceil((i+1) L/bins)) */
+int xv2_adaptive_avgpool_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t bins,
+                             int32_t dtype, void* stream);
+int xv2_adaptive_avgpool_bwd(const void* dy, void* dx, int32_t n, int32_t h, int32_t w, int32_t c, int32_t bins,
+                             int32_t dtype, void* stream);
+/* F.interpolate(mode="bilinear", align_corners=True) (layers.py:27, :154, :186-188): (n,h,w,c) -> (n,oh,ow,c) */
+int xv2_bilinear_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh, int32_t ow,
+                     int32_t dtype, void* stream);
+/* its gradient, accumulated into a ZERO-FILLED fp32 buffer dx_f32[n][h][w][c] (fp32 atomics) */
+int xv2_bilinear_bwd(const void* dy, float* dx_f32, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh, int32_t ow,
+                     int32_t dtype, void* stream);
+/* Ordinal damage heads (unet.py:21-26).  mode 0: 'mse' -- nn.MSELoss(relu(logit[0]), label) (loss.py:92-94), 1 logit per pixel;
+ * mode 1: 'coral' (loss.py:54-65), 3 rank logits per pixel.  `post` masking as loss.py:86-90.
+ * partials: sums fp64 [2] += (loss sum, kept pixels); finalize: loss = weight * sum / pixels, coef[0] = weight / pixels;
+ * backward: dlogits = upstream[0] * d(loss)/d(logits), zero outside the mask. */
+int xv2_ordinal_loss_partials(const float* logits, const uint8_t* labels, int64_t pixels, int32_t mode, int32_t post,
+                              double* sums, void* stream);
+int xv2_ordinal_loss_finalize(const double* sums, float weight, float* loss, float* coef, void* stream);
+int xv2_ordinal_loss_backward(const float* logits, const uint8_t* labels, int64_t pixels, int32_t mode, int32_t post,
+                              const float* coef, const float* upstream, float* dlogits, void* stream);
+/* convert_to_labels (utils/f1.py:7-15): mode 0 -> round(relu(x0)) + 1 (clamped to 4 when clamp4, as F1 does; Model.save
+ * plt.py:131 does not clamp), mode 1 -> #(sigmoid(x_c) > 0.5) + 1.  Any of: F1 counters int64 [12] = tp | fp | fn over pixels
+ * with label > 0 (utils/f1.py:31-42), a uint8 label map, an fp32 label map (what Model.save stores). */
+int xv2_ordinal_labels(const float* logits, const uint8_t* labels, int64_t pixels, int32_t mode, int32_t clamp4,
+                       int64_t* counters, uint8_t* pred_u8, float* pred_f32, void* stream);
+
 /* 1x1 output head (layers.py:180): logits[p][ncls] (fp32) = x[p][c] . w[ncls][c] + b ; ncls <= 8 */
 int xv2_head_fwd(const void* x, const float* w, const float* b, float* logits, int64_t pixels, int32_t c,
                  int32_t ncls, int32_t dtype, void* stream);

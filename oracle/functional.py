@@ -46,9 +46,13 @@ def attention_layer(P, k, x, training):
     return _bn(P, k + ".batch_norm", F.conv2d(x, P[k + ".conv.weight"]), training)
 
 
-def upsample_block(P, k, x, skip, training, attention):
-    """UpsampleBlock (transposed-conv flavour).  layers.py:152-168"""
-    out = F.conv_transpose2d(x, P[k + ".conv_tranpose.conv.weight"], None, 2)  # layers.py:83,156 (attribute typo is the key)
+def upsample_block(P, k, x, skip, training, attention, dec_interp=False):
+    """UpsampleBlock.  layers.py:152-168 (transposed-conv flavour; --dec_interp: 3x3 conv + bias then bilinear x2, :153-154)"""
+    if dec_interp:
+        out = F.interpolate(F.conv2d(x, P[k + ".conv.weight"], P[k + ".conv.bias"], 1, 1), scale_factor=2, mode="bilinear",
+                            align_corners=True)
+    else:
+        out = F.conv_transpose2d(x, P[k + ".conv_tranpose.conv.weight"], None, 2)  # layers.py:83,156 (attribute typo is the key)
     if skip is None:  # skip_channels == 0, layers.py:158-159
         return conv_block(P, k + ".conv_block", out, training)
     if attention:  # layers.py:161-166
@@ -56,6 +60,26 @@ def upsample_block(P, k, x, skip, training, attention):
         psi = attention_layer(P, k + ".psi", F.relu(a), training)
         skip = skip * torch.sigmoid(psi)
     return conv_block(P, k + ".conv_block", torch.cat((out, skip), 1), training)
+
+
+def ppm(P, k, x, training):
+    """PPM (layers.py:6-29): bins 1,2,3,6 -> 1x1 conv -> BN -> LeakyReLU -> bilinear (align_corners) back, cat, 1x1 conv + bias."""
+    outs = [x]
+    for i, b in enumerate((1, 2, 3, 6)):
+        f = F.conv2d(F.adaptive_avg_pool2d(x, b), P[f"{k}.features.{i}.1.weight"])
+        f = F.leaky_relu(_bn(P, f"{k}.features.{i}.2", f, training), 0.01)
+        outs.append(F.interpolate(f, x.shape[2:], mode="bilinear", align_corners=True))
+    return F.conv2d(torch.cat(outs, 1), P[k + ".conv.weight"], P[k + ".conv.bias"])
+
+
+def aspp(P, k, x, training, dilation):
+    """ASPP (layers.py:32-65): 1x1 and three dilated 3x3 (3, 6, 9 x dilation) conv -> BN -> LeakyReLU branches, cat."""
+    outs = []
+    for i, d in enumerate((1, 3 * dilation, 6 * dilation, 9 * dilation)):
+        w = P[f"{k}.aspp{i + 1}.conv.weight"]
+        y = F.conv2d(x, w) if i == 0 else F.conv2d(x, w, None, 1, d, d)
+        outs.append(F.leaky_relu(_bn(P, f"{k}.aspp{i + 1}.bn", y, training), 0.01))
+    return torch.cat(outs, 1)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -184,44 +208,128 @@ def encoder_stage(P, name, i, x, training, encoder, dilation=1):
 # --------------------------------------------------------------------------------------------------------------
 
 
-def decoder_forward(P, names, encs, training, attention):
-    """UNetTemplate.forward decoder half for dilation 1 (unet.py:153-159); names = dec_l1..dec_l5 prefixes."""
+def decoder_forward(P, names, encs, training, attention, dilation=1, no_skip=False, dec_interp=False):
+    """Decoder half of UNetTemplate.forward (unet.py:153-170); names = dec_l1..dec_l5 prefixes.  --dilation 2 / 4 drop the
+    first one / two stages, --no_skip feeds no encoder features."""
     enc1, enc2, enc3, enc4, enc5 = encs
-    d1 = upsample_block(P, names[0], enc5, enc4, training, attention)
-    d2 = upsample_block(P, names[1], d1, enc3, training, attention)
-    d3 = upsample_block(P, names[2], d2, enc2, training, attention)
-    d4 = upsample_block(P, names[3], d3, enc1, training, attention)
-    d5 = upsample_block(P, names[4], d4, None, training, attention)
-    return d5, d4, d3
+    first = {1: 0, 2: 1, 4: 2}[dilation]
+    skips = [enc4, enc3, enc2, enc1, None]
+    x, outs = enc5, {}
+    for i in range(first, 5):
+        x = upsample_block(P, names[i], x, None if no_skip else skips[i], training, attention, dec_interp)
+        outs[i] = x
+    return outs[4], outs[3], outs[2]
+
+
+def _opt(args, name, default=False):
+    return getattr(args, name, default)
+
+
+def _context(P, k, enc5, training, args, suffix=""):
+    """--ppm / --aspp on the last encoder stage (unet.py:144-147)."""
+    if _opt(args, "ppm"):
+        return ppm(P, k + "ppm" + suffix, enc5, training)
+    if _opt(args, "aspp"):
+        return aspp(P, k + "aspp" + suffix, enc5, training, _opt(args, "dilation", 1))
+    return enc5
 
 
 def unet_template(P, k, x, training, args):
-    """UNetTemplate.forward, dilation 1, no ppm/aspp/interpolate (unet.py:136-172) -> (dec5, dec4, dec3)."""
-    encs = encoder_forward(P, k, x, training, args.encoder, 1)
-    return decoder_forward(P, [k + f"dec_l{i}" for i in range(1, 6)], encs, training, args.attention)
+    """UNetTemplate.forward (unet.py:136-172) -> (dec5, dec4, dec3); --interpolate returns (enc5, None, None)."""
+    dil = _opt(args, "dilation", 1)
+    encs = encoder_forward(P, k, x, training, args.encoder, dil)
+    encs[4] = _context(P, k, encs[4], training, args)
+    if _opt(args, "interpolate"):
+        return encs[4], None, None
+    return decoder_forward(P, [k + f"dec_l{i}" for i in range(1, 6)], encs, training, args.attention, dil,
+                           _opt(args, "no_skip"), _opt(args, "dec_interp"))
 
 
-def output_template(P, k, dec5, dec4, dec3, training, deep_supervision):
-    """OutputTemplate.forward (unet.py:191-197): 1x1 conv + bias heads; DS heads only in training."""
-    head = lambda n, t: F.conv2d(t, P[f"{k}.{n}.conv.weight"], P[f"{k}.{n}.conv.bias"])
-    out = head("output_block", dec5)
-    if training and deep_supervision:
-        return [out, head("output_block_ds4", dec4), head("output_block_ds3", dec3)]
+def output_block(P, k, x, training, interpolate=False):
+    """OutputBlock.forward (layers.py:182-189): 1x1 conv (+ bias | + the CORAL rank biases), optional bilinear resize."""
+    if (k + ".bias") in P:  # coral head: 1-channel conv without bias + a (3, 1, 1) bias parameter (layers.py:175-178)
+        out = F.conv2d(x, P[k + ".conv.weight"]) + P[k + ".bias"]
+    else:
+        out = F.conv2d(x, P[k + ".conv.weight"], P[k + ".conv.bias"])
+    if interpolate:
+        out = F.interpolate(out, (512, 512) if training else (1024, 1024), mode="bilinear", align_corners=True)
     return out
+
+
+def output_template(P, k, dec5, dec4, dec3, training, deep_supervision, interpolate=False):
+    """OutputTemplate.forward (unet.py:191-197): heads; DS heads only in training (and never with --interpolate, :181-182)."""
+    out = output_block(P, f"{k}.output_block", dec5, training, interpolate)
+    if training and deep_supervision and not interpolate:
+        return [out, output_block(P, f"{k}.output_block_ds4", dec4, training), output_block(P, f"{k}.output_block_ds3", dec3, training)]
+    return out
+
+
+def _cat(a, b):
+    """concat (unet.py:17-18)."""
+    return None if a is None or b is None else torch.cat([a, b], 1)
 
 
 def unet_loc(P, x, training, args, prefix=""):
     """UNetLoc.forward (unet.py:212-215)."""
     d5, d4, d3 = unet_template(P, prefix + "unet.", x, training, args)
-    return output_template(P, prefix + "output_block", d5, d4, d3, training, args.deep_supervision)
+    return output_template(P, prefix + "output_block", d5, d4, d3, training, args.deep_supervision, _opt(args, "interpolate"))
 
 
 def siamese_unet(P, x, training, args, prefix=""):
     """SiameseUNet.forward (unet.py:231-236): the SAME U-Net on pre then post (separate BN statistics), cat, heads."""
     pre = unet_template(P, prefix + "unet.", x[:, :3], training, args)
     post = unet_template(P, prefix + "unet.", x[:, 3:], training, args)
-    d5, d4, d3 = (torch.cat([a, b], 1) for a, b in zip(pre, post))
-    return output_template(P, prefix + "output_block", d5, d4, d3, training, args.deep_supervision)
+    d5, d4, d3 = (_cat(a, b) for a, b in zip(pre, post))
+    return output_template(P, prefix + "output_block", d5, d4, d3, training, args.deep_supervision, _opt(args, "interpolate"))
+
+
+def _twin_decode(P, p, pre, post, training, args):
+    encs = [_cat(a, b) for a, b in zip(pre, post)]
+    d5, d4, d3 = decoder_forward(P, [p + f"dec_l{i}" for i in range(1, 6)], encs, training, args.attention,
+                                 _opt(args, "dilation", 1), _opt(args, "no_skip"), _opt(args, "dec_interp"))
+    return output_template(P, p + "output_block", d5, d4, d3, training, args.deep_supervision)
+
+
+def siamese_enc_unet(P, x, training, args, prefix=""):
+    """SiameseEncUNet.forward (unet.py:275-314): one shared ENCODER on pre and post, features concatenated, one decoder."""
+    p, dil = prefix, _opt(args, "dilation", 1)
+    feats = []
+    for part in (x[:, :3], x[:, 3:]):
+        encs = encoder_forward(P, p, part, training, args.encoder, dil)
+        encs[4] = _context(P, p, encs[4], training, args)
+        feats.append(encs)
+    return _twin_decode(P, p, feats[0], feats[1], training, args)
+
+
+def parallel_unet(P, x, training, args, prefix=""):
+    """ParallelUNet.forward (unet.py:441-446) with its quirk: BOTH halves are unet_pre on the PRE image."""
+    first = unet_template(P, prefix + "unet_pre.", x[:, :3], training, args)
+    second = unet_template(P, prefix + "unet_pre.", x[:, :3], training, args)
+    d5, d4, d3 = (_cat(a, b) for a, b in zip(first, second))
+    return output_template(P, prefix + "output_block", d5, d4, d3, training, args.deep_supervision, _opt(args, "interpolate"))
+
+
+def parallel_enc_unet(P, x, training, args, prefix=""):
+    """ParallelEncUNet.forward (unet.py:497-540): separate pre / post encoders, features concatenated, one decoder."""
+    p, dil = prefix, _opt(args, "dilation", 1)
+    feats = []
+    for part, tag in ((x[:, :3], "pre"), (x[:, 3:], "post")):
+        encs = encoder_forward_named(P, [f"{p}enc_l{i}_{tag}" for i in range(1, 6)], part, training, args.encoder, dil)
+        encs[4] = _context(P, p, encs[4], training, args, "_" + tag)
+        feats.append(encs)
+    if _opt(args, "interpolate"):
+        return output_template(P, p + "output_block", _cat(feats[0][4], feats[1][4]), None, None, training, False, True)
+    return _twin_decode(P, p, feats[0], feats[1], training, args)
+
+
+def diff_unet(P, x, training, args, prefix=""):
+    """DiffUNet.forward (unet.py:548-551)."""
+    return unet_loc(P, x[:, :3] - x[:, 3:], training, args, prefix + "unet.")
+
+
+def cat_unet(P, x, training, args, prefix=""):
+    """CatUNet.forward (unet.py:558-560) with the 6-channel stem the reference intended (its constructor raises)."""
+    return unet_loc(P, x, training, args, prefix + "unet.")
 
 
 def _fusion(P, k, pre, post, training):
@@ -254,15 +362,30 @@ def fused_unet(P, x, training, args, prefix=""):
     return output_template(P, p + "output_block", d5, d4, d3, training, args.deep_supervision)
 
 
+def fused_enc_unet(P, x, training, args, prefix=""):
+    """FusedEncUNet.forward (unet.py:411-426): fused twin encoders, ONE decoder fed with the post branch."""
+    p = prefix
+    pre, post = x[:, :3], x[:, 3:]
+    e_post = []
+    for i in range(5):
+        pre = encoder_stage(P, f"{p}enc_l{i+1}_pre", i, pre, training, args.encoder, 1)
+        post = encoder_stage(P, f"{p}enc_l{i+1}_post", i, post, training, args.encoder, 1)
+        pre, post = _fusion(P, f"{p}fusion_block{i+1}", pre, post, training)
+        e_post.append(post)
+    d5, d4, d3 = decoder_forward(P, [p + f"dec_l{i}" for i in range(1, 6)], e_post, training, args.attention, 1,
+                                 _opt(args, "dec_interp"))  # dec_interp sits in get_decoder's no_skip slot (unet.py:398-400)
+    return output_template(P, p + "output_block", d5, d4, d3, training, args.deep_supervision)
+
+
 def model_forward(P, x, training, args, prefix=""):
-    """Model.__init__ dispatch (plt.py:26) for the variants BASELINE.json names."""
+    """Model.__init__ dispatch (plt.py:26; get_dmg_unet unet.py:29-42)."""
     if args.type == "pre":
         return unet_loc(P, x, training, args, prefix)
-    if args.dmg_model == "siamese":
-        return siamese_unet(P, x, training, args, prefix)
-    if args.dmg_model == "fused":
-        return fused_unet(P, x, training, args, prefix)
-    raise NotImplementedError(args.dmg_model)
+    table = {"siamese": siamese_unet, "siameseEnc": siamese_enc_unet, "fused": fused_unet, "fusedEnc": fused_enc_unet,
+             "parallel": parallel_unet, "parallelEnc": parallel_enc_unet, "diff": diff_unet, "cat": cat_unet}
+    if args.dmg_model not in table:
+        raise NotImplementedError(args.dmg_model)
+    return table[args.dmg_model](P, x, training, args, prefix)
 
 
 def tta_forward(P, x, args, prefix=""):
@@ -298,6 +421,25 @@ def ce_loss(logits2d, target1d):
     return F.cross_entropy(logits2d, target1d)
 
 
+CORAL_LEVELS = torch.tensor([[0, 0, 0], [1, 0, 0], [1, 1, 0], [1, 1, 1]], dtype=torch.float32)
+
+
+def coral_loss(logits2d, target1d):
+    """CORAL (loss.py:54-65) on flattened (M, 3) rank logits / (M,) labels 0..3."""
+    levels = CORAL_LEVELS.to(logits2d.device)[target1d]
+    logpt = F.logsigmoid(logits2d)
+    return -torch.mean(torch.sum(logpt * levels + (logpt - logits2d) * (1 - levels), dim=1))
+
+
+def convert_to_labels(loss_str, logits):
+    """utils/f1.py:7-15."""
+    if loss_str == "mse":
+        return torch.round(F.relu(logits[:, 0])).clamp_max(3) + 1
+    if loss_str == "coral":
+        return torch.sum(torch.sigmoid(logits) > 0.5, dim=1) + 1
+    return torch.argmax(logits, dim=1) + 1
+
+
 def loss_forward(y_pred, y_true, loss_str, post):
     """Loss.forward (loss.py:85-101).  `post` keeps only pixels with label > 0 and shifts labels by -1.
 
@@ -310,6 +452,10 @@ def loss_forward(y_pred, y_true, loss_str, post):
     if post:
         keep = tgt > 0
         flat, tgt = flat[keep], tgt[keep] - 1
+    if loss_str == "mse":  # loss.py:92-94: relu on channel 0, float targets, nn.MSELoss
+        return F.mse_loss(F.relu(flat[:, 0]), tgt.float())
+    if loss_str == "coral":
+        return coral_loss(flat, tgt)
     total = 0
     for name in loss_str.split("+"):
         if name == "dice":

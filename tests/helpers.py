@@ -58,3 +58,13 @@ def check_digest(t, dg, rtol, atol_scale=1.0):
 def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def sub_logits(t, fx):
+    """Applies the fixture's logit sub-sampling (--interpolate fixtures keep every 16th row / column) to a model output."""
+    st = fx.get("logit_stride", 1)
+    if st == 1:
+        return t
+    if isinstance(t, (list, tuple)):
+        return [o[..., ::st, ::st] for o in t]
+    return t[..., ::st, ::st]

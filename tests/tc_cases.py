@@ -44,6 +44,15 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
+def ulp_excess(out_bf16, ref_fp32):
+    """How far a bf16 result is from the fp32 reference BEYOND one bf16 ulp of each element (2^-8 relative: rounding of the
+    fp32 accumulator plus a one-ulp difference in where the accumulation-order noise lands), relative to the largest
+    reference magnitude.  ~1e-5 for a correct kernel (fp32 accumulation-order noise); a dropped K block shows up as O(0.1)."""
+    a, b = out_bf16.detach().double().cpu(), ref_fp32.detach().double().cpu()
+    exc = ((a - b).abs() - b.abs() * 2.0 ** -8).clamp_min(0.0)
+    return float(exc.max() / b.abs().max().clamp_min(1e-12))
+
+
 def _rnd(shape, seed, scale=1.0):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(*shape, generator=g) * scale).cuda()
@@ -96,11 +105,44 @@ def run_case(name, check_wgrad=True, check_dgrad=True):
         x2r = None
         yr = F.conv_transpose2d(xr, wr, None, 2)
     yr.backward(gy.float())
-    out = {"fwd": rel(y, yr)}
+    out = {"fwd": rel(y, yr), "fwd_ulp": ulp_excess(y, yr)}
     if check_dgrad:
         out["dgrad"] = rel(x.grad, xr.grad)
+        out["dgrad_ulp"] = ulp_excess(x.grad, xr.grad)
         if c1:
             out["dgrad2"] = rel(x2.grad, x2r.grad)
+            out["dgrad2_ulp"] = ulp_excess(x2.grad, x2r.grad)
     if check_wgrad:
         out["wgrad"] = rel(wt.grad, wr.grad)
     return out
+
+
+def run_f32_case(name):
+    """The same tcgen05 main loop with its fp32-output epilogue, called straight through the C ABI (xv2_conv_tc with
+    out_dtype = XV2_F32): exact bf16 operands, fp32 TMEM accumulation, no output rounding -> the only difference from
+    torch's fp32 convolution on the same operands is the summation order.  Returns the relative error (max |d| / max |ref|)."""
+    from xview2_b200 import lib, ops
+    from xview2_b200.lib import BF16, F32, TcConv, call, ptr
+    kind, n, c0, c1, h, w, k, r, dil, groups = CASES[name]
+    lib.init(torch.cuda.current_device())
+    x = _rnd((n, c0, h, w), 1).to(torch.bfloat16).contiguous(memory_format=CL)
+    x2 = _rnd((n, c1, h, w), 2).to(torch.bfloat16).contiguous(memory_format=CL) if c1 else None
+    if kind == "conv":
+        cg = (c0 + c1) // groups
+        wt = _rnd((k, cg, r, r), 3, (2.0 / (cg * r * r)) ** 0.5).contiguous(memory_format=CL)
+        pad = dil * (r - 1) // 2
+        wp = ops.pack_weight(wt, 0, torch.bfloat16, groups)
+        out = torch.empty((n, k, h, w), dtype=torch.float32, device="cuda").contiguous(memory_format=CL)
+        p = TcConv(n, h, w, c0, c1, 0, 0, k, r, r, pad, dil, groups, 0, F32, 0)
+        call("xv2_conv_tc", p, ptr(x), ptr(x2), ptr(wp), None, ptr(out), None)
+        src = x.float() if x2 is None else torch.cat((x.float(), x2.float()), 1)
+        ref = F.conv2d(src, wt.to(torch.bfloat16).float(), None, 1, pad, dil, groups)
+    else:
+        wt = _rnd((c0, k, 2, 2), 3, (1.0 / c0) ** 0.5).contiguous(memory_format=CL)
+        wp = ops.pack_weight(wt, 2, torch.bfloat16)
+        out = torch.empty((n, k, 2 * h, 2 * w), dtype=torch.float32, device="cuda").contiguous(memory_format=CL)
+        p = TcConv(n, h, w, c0, 0, 0, 0, k, 1, 1, 0, 1, 1, 1, F32, 0)
+        call("xv2_conv_tc", p, ptr(x), None, ptr(wp), None, ptr(out), None)
+        ref = F.conv_transpose2d(x.float(), wt.to(torch.bfloat16).float(), None, 2)
+    torch.cuda.synchronize()
+    return rel(out, ref)

@@ -385,3 +385,108 @@ def test_mean4_and_normalize_and_adamw():
         opt.step()
         ops.adamw_step(p, gq, m_, v_, 3e-4, 0.9, 0.999, 1e-8, 0.01, step)
     assert rel(p, pr.data) < 1e-5
+
+
+@pytest.mark.parametrize("ncls", [2, 4])
+def test_save_probs_values_vs_reference_formula(ncls):
+    """Model.save (plt.py:126-131): sigmoid(pred[:, 1]) for the localisation head, softmax(pred, 1) (planar NCHW, the layout
+    np.save receives) for the damage head -- VALUES against torch, not just range / shape."""
+    ops = _ops()
+    logits = rnd(3, ncls, 40, 56, seed=21, scale=3.0).contiguous(memory_format=CL)
+    got = ops.save_probs(logits)
+    ref = torch.sigmoid(logits[:, 1]) if ncls == 2 else torch.softmax(logits, 1)
+    assert got.shape == ref.shape and got.dtype == torch.float32 and got.is_contiguous()
+    assert float((got - ref).abs().max()) < 2e-6
+    if ncls == 4:
+        assert float((got.sum(1) - 1).abs().max()) < 1e-5
+    # bf16 logits (what the tensor-core path hands over) go through the same kernel after an exact up-cast
+    got16 = ops.save_probs(logits.to(torch.bfloat16))
+    ref16 = torch.sigmoid(logits.to(torch.bfloat16).float()[:, 1]) if ncls == 2 else torch.softmax(logits.to(torch.bfloat16).float(), 1)
+    assert float((got16 - ref16).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("bins,hw", [(1, (5, 7)), (2, (4, 4)), (3, (8, 10)), (6, (16, 16)), (6, (7, 9))])
+def test_adaptive_avg_pool(dtype, bins, hw):
+    """PPM's nn.AdaptiveAvgPool2d (layers.py:13) forward / backward vs torch."""
+    ops = _ops()
+    x = rnd(2, 24, *hw, dtype=dtype, seed=3).contiguous(memory_format=CL).requires_grad_(True)
+    y = ops.adaptive_avg_pool2d(x, bins)
+    gy = rnd(*y.shape, dtype=dtype, seed=4).contiguous(memory_format=CL)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    yr = F.adaptive_avg_pool2d(xr, bins)
+    yr.backward(gy.float())
+    assert rel(y, yr) < tol(dtype) and rel(x.grad, xr.grad) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("hw,out", [((1, 1), (8, 8)), ((2, 2), (8, 8)), ((3, 6), (16, 16)), ((16, 16), (32, 32)), ((8, 8), (64, 64)),
+                                    ((16, 12), (5, 7))])
+def test_bilinear_align_corners(dtype, hw, out):
+    """F.interpolate(mode='bilinear', align_corners=True) (layers.py:27,154,188) forward / backward vs torch."""
+    ops = _ops()
+    x = rnd(2, 12, *hw, dtype=dtype, seed=7).contiguous(memory_format=CL).requires_grad_(True)
+    y = ops.bilinear(x, out)
+    gy = rnd(*y.shape, dtype=dtype, seed=8).contiguous(memory_format=CL)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    yr = F.interpolate(xr, out, mode="bilinear", align_corners=True)
+    yr.backward(gy.float())
+    assert rel(y, yr) < tol(dtype) and rel(x.grad, xr.grad) < tol(dtype)
+
+
+@pytest.mark.parametrize("loss_str,post", [("mse", True), ("coral", True), ("coral", False), ("mse", False)])
+def test_ordinal_heads_vs_oracle(loss_str, post):
+    """'mse' / 'coral' damage heads: loss + gradient (loss.py:54-65,86-94) and label decoding + F1 counters (utils/f1.py:7-42)."""
+    from oracle import functional as OF
+    ops = _ops()
+    nl = 1 if loss_str == "mse" else 3
+    g = torch.Generator().manual_seed(13)
+    logits = (torch.randn(3, nl, 24, 40, generator=g) * 2).cuda().contiguous(memory_format=CL).requires_grad_(True)
+    hi = 5 if post else 4
+    labels = torch.randint(0, hi, (3, 24, 40), generator=g, dtype=torch.uint8).cuda()
+    loss = ops.seg_loss(logits, labels, loss_str, post, weight=0.5)
+    loss.backward()
+    lr = logits.detach().cpu().requires_grad_(True)
+    ref = 0.5 * OF.loss_forward(lr, labels.cpu(), loss_str, post)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert rel(logits.grad, lr.grad) < 1e-5
+    # decoding: exact integers
+    got = ops.ordinal_labels(logits, loss_str, want_u8=True).cpu().long()
+    want = OF.convert_to_labels(loss_str, logits.detach().cpu()).long()
+    assert torch.equal(got, want)
+    if post:
+        counters = torch.zeros(12, dtype=torch.int64, device="cuda")
+        ops.ordinal_labels(logits, loss_str, labels, counters)
+        t = labels.cpu().long()
+        keep = t > 0
+        for c in range(1, 5):
+            tp = int(((want == c) & (t == c) & keep).sum())
+            fp = int(((want == c) & (t != c) & keep).sum())
+            fn = int(((want != c) & (t == c) & keep).sum())
+            assert (int(counters[c - 1]), int(counters[4 + c - 1]), int(counters[8 + c - 1])) == (tp, fp, fn)
+
+
+def test_cat_unet_matches_oracle():
+    """CatUNet (unet.py:554-560): the reference's constructor raises; the 6-channel stem it intended is checked
+    against the oracle's functional U-Net given the same weights."""
+    import argparse
+
+    from oracle import functional as OF
+    from xview2_b200.model.unet import get_dmg_unet
+    ns = argparse.Namespace(ppm=False, aspp=False, dilation=1, no_skip=False, interpolate=False, attention=False, dec_interp=False,
+                            deep_supervision=False, loss_str="focal+dice", encoder="resnest50", dmg_model="cat", type="post",
+                            tta=False, precision=32)
+    model = get_dmg_unet(ns)
+    shapes = {k: (tuple(v.shape), v.dtype) for k, v in model.state_dict().items()}
+    state = OF.deterministic_state(shapes, 1)
+    model.load_state_dict(state, strict=True)
+    model = model.cuda().train()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(4, 6, 64, 64, generator=g)
+    out = model(x.cuda())
+    ref = OF.model_forward({k: v.clone() for k, v in state.items()}, x, True, ns)
+    assert out.shape == ref.shape == (4, 4, 64, 64)
+    assert rel(out, ref) < 1e-3

@@ -16,7 +16,7 @@ bf16 path  : same network on the tcgen05 kernels; tolerance 6e-2 of the logit ra
 import pytest
 import torch
 
-from tests.helpers import check_digest, golden_inputs, golden_names, golden_state, load_golden, rel_err
+from tests.helpers import check_digest, golden_inputs, golden_names, golden_state, load_golden, rel_err, sub_logits
 
 pytestmark = pytest.mark.gpu
 
@@ -48,6 +48,21 @@ def _as_list(t):
     return t if isinstance(t, list) else [t]
 
 
+def _decisions(logits, ref, band, loss_str):
+    """(ours, reference, clear) decoded label maps and the mask of pixels whose reference decision is at least `band` (absolute
+    logit units) away from flipping: argmax for the soft-max heads, utils/f1.py:7-15 decoding for the mse / coral heads."""
+    from oracle import functional as OF
+    logits, ref = logits.detach().float().cpu(), ref.float()
+    if loss_str == "mse":
+        r = torch.relu(ref[:, 0])
+        clear = ((r - torch.floor(r) - 0.5).abs() > band) & ((ref[:, 0].abs() > band) | (ref[:, 0] < -band))
+        return OF.convert_to_labels("mse", logits), OF.convert_to_labels("mse", ref), clear
+    if loss_str == "coral":
+        return OF.convert_to_labels("coral", logits), OF.convert_to_labels("coral", ref), (ref.abs() > band).all(1)
+    top2 = ref.topk(2, dim=1).values
+    return logits.argmax(1), ref.argmax(1), (top2[:, 0] - top2[:, 1]) > band
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_fp32_parity(name):
     fx = load_golden(name)
@@ -55,17 +70,16 @@ def test_fp32_parity(name):
     x, y = golden_inputs(fx)
     model.eval()
     with torch.no_grad():
-        ev = model(x.cuda())
+        ev = sub_logits(model(x.cuda()), fx)
     ref, ref64 = fx["eval_logits"], fx["eval_logits64"]
     tol = max(1e-3, NOISE_X * rel_err(ref, ref64))
     assert rel_err(ev, ref64) < tol and rel_err(ev, ref) < tol, (rel_err(ev, ref64), rel_err(ev, ref), tol)
-    top2 = ref64.topk(2, dim=1).values
-    margin = (top2[:, 0] - top2[:, 1]) > tol * float(ref64.abs().max())
-    same = ev.argmax(1).cpu() == ref64.argmax(1)
-    assert bool(same[margin].all()), f"{int((~same[margin]).sum())} argmax mismatches outside the tie band"
+    ours, theirs, margin = _decisions(ev, ref64, tol * float(ref64.abs().max()), fx["ns"].loss_str)
+    same = ours == theirs
+    assert bool(same[margin].all()), f"{int((~same[margin]).sum())} label-map mismatches outside the tie band"
 
     out, loss = run_train(fx, model)
-    for o, r, r64 in zip(_as_list(out), _as_list(fx["train_logits"]), _as_list(fx["train_logits64"])):
+    for o, r, r64 in zip(_as_list(sub_logits(out, fx)), _as_list(fx["train_logits"]), _as_list(fx["train_logits64"])):
         tol = max(1e-3, NOISE_X * rel_err(r, r64))
         assert rel_err(o, r64) < tol, (rel_err(o, r64), tol)
     ltol = max(1e-4 * max(1.0, abs(fx["loss64"])), NOISE_X * abs(fx["loss"] - fx["loss64"]))
@@ -104,7 +118,7 @@ def _amp_yardstick(fx):
         P = {k: v.cuda() for k, v in golden_state(fx).items()}
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             out = OF.model_forward(P, x.cuda(), training, ns)
-        errs.append(max(rel_err(o.float(), r) for o, r in zip(_as_list(out), _as_list(fx[key]))))
+        errs.append(max(rel_err(o.float(), r) for o, r in zip(_as_list(sub_logits(out, fx)), _as_list(fx[key]))))
     return errs[0], errs[1]
 
 
@@ -117,17 +131,25 @@ def test_bf16_parity(name):
     x, y = golden_inputs(fx)
     model.eval()
     with torch.no_grad():
-        ev = model(x.cuda())
+        ev = sub_logits(model(x.cuda()), fx)
     ref = fx["eval_logits64"]
     err = rel_err(ev, ref)
     out, loss = run_train(fx, model)
-    terr = max(rel_err(o, r) for o, r in zip(_as_list(out), _as_list(fx["train_logits64"])))
+    terr = max(rel_err(o, r) for o, r in zip(_as_list(sub_logits(out, fx)), _as_list(fx["train_logits64"])))
     lerr = abs(float(loss.detach()) - fx["loss64"]) / max(1.0, abs(fx["loss64"]))
-    agree = float((ev.argmax(1).cpu() == ref.argmax(1)).float().mean())
     amp_eval, amp_train = _amp_yardstick(fx)
+    bound = max(6e-2, 1.5 * amp_eval)
+    # the label map of the BENCHMARKED (tcgen05) path: bit-exact wherever the reference's own decision margin exceeds twice the
+    # logit tolerance (both competing logits may move by the bound), and an overall agreement floor
+    ours, theirs, clear = _decisions(ev, ref, 2 * bound * float(ref.abs().max()), fx["ns"].loss_str)
+    same = ours == theirs
+    agree = float(same.float().mean())
     print(f"\n[bf16 {name}] eval logits {err:.4f} (torch autocast {amp_eval:.4f}) train logits {terr:.4f} "
-          f"(torch autocast {amp_train:.4f}) loss {lerr:.5f} argmax agreement {agree:.4f}")
-    assert err < max(6e-2, 1.5 * amp_eval) and terr < max(6e-2, 1.5 * amp_train) and lerr < 3e-2
+          f"(torch autocast {amp_train:.4f}) loss {lerr:.5f} argmax agreement {agree:.4f} "
+          f"(clear-margin pixels: {float(clear.float().mean()):.3f} of the map)")
+    assert err < bound and terr < max(6e-2, 1.5 * amp_train) and lerr < 3e-2
+    assert bool(same[clear].all()), f"{int((~same[clear]).sum())} argmax mismatches outside the tie band on the bf16 path"
+    assert agree >= 0.9, f"bf16 argmax agreement {agree:.4f} below the floor"
 
 
 def test_cuda_graph_step_matches_eager():

@@ -6,11 +6,29 @@ from tests.tc_cases import CASES, run_case
 pytestmark = pytest.mark.gpu
 
 
+from tests.tc_cases import run_f32_case  # noqa: E402
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_tc_conv(name):
+    """bf16-output kernels: every element within ONE bf16 ulp of torch's fp32 result on the same bf16 operands (+ 5e-4 of the
+    largest magnitude for fp32 accumulation-order noise); the fp32 weight gradient within 1e-3.  A kernel that drops a K block,
+    a tap or a halo column fails these by orders of magnitude (the former 2e-2 bound would not have caught a deep-layer drop)."""
     errs = run_case(name)
     for key, val in errs.items():
-        assert val < 2e-2, (name, errs)
+        if key.endswith("_ulp"):
+            assert val < 5e-4, (name, key, errs)
+        elif key == "wgrad":
+            assert val < 1e-3, (name, key, errs)
+        else:
+            assert val < 8e-3, (name, key, errs)  # one bf16 ulp (2^-8 = 3.9e-3) of the largest element, plus slack
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if not n.startswith("strip_")])
+def test_tc_conv_f32_output(name):
+    """fp32-output epilogue of the same tcgen05 main loop (north_star: 1e-3 on fp32 logits): <= 1e-3, expected ~1e-5."""
+    err = run_f32_case(name)
+    assert err < 1e-3, (name, err)
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 0, 64, 256, 32, 1, 3), (2, 64, 64, 24, 128, 64, 1, 3), (1, 128, 0, 40, 128, 256, 2, 3),
@@ -35,6 +53,7 @@ def test_conv_stats_epilogue(shape):
     import torch.nn.functional as F
     src = x.float() if x2 is None else torch.cat((x.float(), x2.float()), 1)
     yr = F.conv2d(src, wt.to(torch.bfloat16).float(), None, 1, r // 2, 1, groups)
-    assert float((out.float() - yr).abs().max() / yr.abs().max()) < 2e-2
+    from tests.tc_cases import ulp_excess
+    assert ulp_excess(out, yr) < 5e-4
     err = float((stats - ref).abs().max() / ref.abs().max())
     assert err < 1e-5, err

@@ -1,0 +1,35 @@
+#!/bin/bash
+# Round-2 GPU-box trips.  Usage (through gpurun): bash tools/gpu_r2.sh [stages...]
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvidia_smi.txt 2>&1
+python -c "import os; print('cpus', os.cpu_count())" >> gpurun_out/nvidia_smi.txt
+STAGES="${*:-tests smoke bench}"
+NCU=/usr/local/cuda/bin/ncu
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+for s in $STAGES; do
+  echo "=== stage $s $(date +%T)"
+  case $s in
+    tests) timeout 2400 python -m pytest tests -q -m gpu --no-header -p no:cacheprovider --tb=short --maxfail=40 -s > gpurun_out/tests.log 2>&1; tail -60 gpurun_out/tests.log | cut -c1-400 ;;
+    tests_x) timeout 2400 python -m pytest tests -q -m gpu --no-header -p no:cacheprovider --tb=short -x > gpurun_out/tests.log 2>&1; tail -30 gpurun_out/tests.log | cut -c1-400 ;;
+    smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log ;;
+    bench) timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -c 2500 gpurun_out/bench_c2.json; tail -5 gpurun_out/bench_c2.err ;;
+    bench_quick) timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-library-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; python tools/show_bench.py gpurun_out/bench_quick.json; tail -5 gpurun_out/bench_quick.err ;;
+    bench_c3|bench_c4|bench_c5) c=${s#bench_}; timeout 1500 python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; python tools/show_bench.py gpurun_out/bench_$c.json; tail -5 gpurun_out/bench_$c.err ;;
+    ref) timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 1200 gpurun_out/bench_ref.json ;;
+    layers) timeout 600 python tools/layer_profile.py > gpurun_out/layers.txt 2> gpurun_out/layers.err; head -3 gpurun_out/layers.txt; tail -3 gpurun_out/layers.err ;;
+    launches) timeout 1200 $NCU --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+        --log-file gpurun_out/launches.csv python tools/layer_profile.py --ncu > gpurun_out/launches.log 2>&1; wc -l gpurun_out/launches.csv ;;
+    traffic) timeout 1500 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+        --profile-from-start off --csv --log-file gpurun_out/traffic.csv python tools/layer_profile.py --ncu > gpurun_out/traffic.log 2>&1; wc -l gpurun_out/traffic.csv ;;
+    ncu_full) # one --set full row per distinct kernel of the step: the first 2 launches of every kernel name
+        timeout 2400 $NCU --set full --clock-control none --import-source on --profile-from-start off --launch-count 2000 \
+        --kernel-id :::1\|2 -f -o gpurun_out/prof_full python tools/layer_profile.py --ncu > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log
+        $NCU -i gpurun_out/prof_full.ncu-rep --page raw --csv > gpurun_out/prof_full_raw.csv 2>/dev/null; wc -l gpurun_out/prof_full_raw.csv ;;
+    scale2|scale4|scale8) n=${s#scale}; for c in ${CFGS:-c2}; do
+        timeout 1500 $TR --nproc-per-node $n --master-port 295$n bench.py --config $c --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_${c}_n$n.json 2> gpurun_out/scale_${c}_n$n.err
+        python tools/show_bench.py gpurun_out/scale_${c}_n$n.json; tail -3 gpurun_out/scale_${c}_n$n.err; done ;;
+    *) echo "unknown stage $s" ;;
+  esac
+done
+echo "=== done $(date +%T)"

@@ -35,6 +35,27 @@ CASES = {
     "c3_resnest101_siamese": (dict(encoder="resnest101", type="post", dmg_model="siamese"), 4, 64),
     "c4_resnest50_fused_ds_attn": (dict(encoder="resnest50", type="post", dmg_model="fused", deep_supervision=True,
                                         attention=True), 4, 64),
+    # BASELINE config 4's encoder at a size the CPU finishes: ResNeSt-200 fused + deep supervision + attention (386 M params)
+    "c4_resnest200_fused_ds_attn": (dict(encoder="resnest200", type="post", dmg_model="fused", deep_supervision=True,
+                                         attention=True, lite=True), 4, 64),
+    # the remaining damage-model variants (unet.py:239-560), "lite" fixtures: logits + loss + sampled digests
+    "v_resnest50_siameseEnc": (dict(type="post", dmg_model="siameseEnc", lite=True), 4, 64),
+    "v_resnest50_fusedEnc": (dict(type="post", dmg_model="fusedEnc", lite=True), 4, 64),
+    "v_resnest50_parallel": (dict(type="post", dmg_model="parallel", lite=True), 4, 64),
+    "v_resnest50_parallelEnc": (dict(type="post", dmg_model="parallelEnc", lite=True), 4, 64),
+    "v_resnet50_diff": (dict(encoder="resnet50", type="post", dmg_model="diff", lite=True), 4, 64),
+    "v_resnest50_dilation2": (dict(dilation=2, lite=True), 4, 64),
+    "v_resnest50_dilation4_noskip": (dict(dilation=4, no_skip=True, lite=True), 4, 64),
+    "v_resnet50_dilation2": (dict(encoder="resnet50", dilation=2, lite=True), 4, 64),
+    # optional model parts (layers.py:6-65,154,175-188; loss.py:54-65,92-94)
+    "f4_resnet50_ppm": (dict(encoder="resnet50", ppm=True, lite=True), 4, 64),
+    "f4_resnest50_aspp": (dict(aspp=True, lite=True), 4, 64),
+    "f4_resnet50_dec_interp": (dict(encoder="resnet50", dec_interp=True, lite=True), 4, 64),
+    # --interpolate resizes the logits to 512^2 (training) / 1024^2 (eval): the input must be a 512^2 crop for the training
+    # loss to be defined; the fixture keeps every 16th logit row / column
+    "f4_resnet50_interpolate": (dict(encoder="resnet50", interpolate=True, lite=True, logit_stride=16), 4, 512),
+    "f4_resnest50_siamese_coral": (dict(type="post", dmg_model="siamese", loss_str="coral", lite=True), 4, 64),
+    "f4_resnet50_siamese_mse": (dict(encoder="resnet50", type="post", dmg_model="siamese", loss_str="mse", lite=True), 4, 64),
 }
 
 
@@ -92,6 +113,13 @@ def forward_backward(model, loss_mod, args, x, y):
             loss = loss + 0.5 ** (i + 1) * loss_mod(pred, ds.squeeze(1))
         loss = loss / (2 - 2 ** (-len(out)))
         train_logits = [o.detach().clone() for o in out]
+    elif args.loss_str == "mse" and out.dtype == torch.float64:
+        # fp64 yard-stick only: Loss.forward casts the target with .float() (loss.py:94), which nn.MSELoss rejects against
+        # fp64 predictions; the same formula (loss.py:86-94) with a double target
+        keep = y > 0
+        pred = torch.relu(torch.stack([out[:, i][keep] for i in range(out.shape[1])], 1)[:, 0])
+        loss = torch.nn.functional.mse_loss(pred, (y[keep] - 1).double())
+        train_logits = out.detach().clone()
     else:
         loss = loss_mod(out, y)
         train_logits = out.detach().clone()
@@ -107,6 +135,9 @@ def rel(a, b):
 
 def run_case(ref_unet, ref_loss, name, over, batch, size):
     import copy
+    over = dict(over)
+    lite = over.pop("lite", False)
+    lstride = over.pop("logit_stride", 1)
     args = argparse.Namespace(**{**BASE, **over})
     model = build_reference_model(ref_unet, args)
     shapes = {k: (tuple(v.shape), v.dtype) for k, v in model.state_dict().items()}
@@ -130,13 +161,22 @@ def run_case(ref_unet, ref_loss, name, over, batch, size):
     uniq64 = {k: (digest(g) if g is not None else None) for k, g in grads64.items()}
     noise = {k: (rel(grads[k], grads64[k]) if grads[k] is not None else None) for k in grads}
     post_state = {k: digest(v.float()) for k, v in model.state_dict().items() if "running_" in k}
+    if lite:  # every 7th parameter / running statistic: keeps the many variant fixtures small
+        keep = set(sorted(uniq)[::7])
+        uniq = {k: v for k, v in uniq.items() if k in keep}
+        uniq64 = {k: v for k, v in uniq64.items() if k in keep}
+        noise = {k: v for k, v in noise.items() if k in keep}
+        post_state = {k: v for k, v in post_state.items() if k in set(sorted(post_state)[::7])}
     as32 = lambda t: [o.float() for o in t] if isinstance(t, list) else t.float()
     l32 = train_logits[0] if isinstance(train_logits, list) else train_logits
     l64 = train_logits64[0] if isinstance(train_logits64, list) else train_logits64
     print(f"  conditioning (reference fp32 vs fp64): eval logits {rel(eval_logits, eval_logits64):.2e}  train logits "
           f"{rel(l32, l64):.2e}  grads median {sorted(v for v in noise.values() if v is not None)[len(noise) // 2]:.2e}")
+    if lstride > 1:
+        sub = lambda t: [o[..., ::lstride, ::lstride].clone() for o in t] if isinstance(t, list) else t[..., ::lstride, ::lstride].clone()
+        eval_logits, eval_logits64, train_logits, train_logits64 = (sub(t) for t in (eval_logits, eval_logits64, train_logits, train_logits64))
     return {
-        "name": name, "args": vars(args), "batch": batch, "size": size, "input_seed": 1, "state_seed": 1,
+        "name": name, "args": vars(args), "batch": batch, "size": size, "input_seed": 1, "state_seed": 1, "logit_stride": lstride,
         "state_shapes": {k: (s, str(d)) for k, (s, d) in shapes.items()},
         "calibrated_running": running,
         "eval_logits": eval_logits, "eval_logits64": eval_logits64.float(),

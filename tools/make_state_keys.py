@@ -31,6 +31,16 @@ CASES = {
     "parallel": dict(type="post", dmg_model="parallel"),
     "parallelEnc": dict(type="post", dmg_model="parallelEnc"),
     "diff": dict(type="post", dmg_model="diff"),
+    # optional model parts (layers.py:6-65,138-139,175-188)
+    "loc_resnet50_ppm": dict(encoder="resnet50", ppm=True),
+    "loc_resnest50_aspp_dil2": dict(aspp=True, dilation=2),
+    "loc_resnet50_dec_interp": dict(encoder="resnet50", dec_interp=True),
+    "loc_resnet50_interpolate": dict(encoder="resnet50", interpolate=True),
+    "siamese_coral": dict(type="post", dmg_model="siamese", loss_str="coral"),
+    "siamese_mse_interpolate": dict(type="post", dmg_model="siamese", loss_str="mse", interpolate=True),
+    "siameseEnc_ppm": dict(type="post", dmg_model="siameseEnc", ppm=True),
+    "parallelEnc_aspp": dict(type="post", dmg_model="parallelEnc", aspp=True),
+    "parallelEnc_ppm_interpolate": dict(type="post", dmg_model="parallelEnc", ppm=True, interpolate=True),
 }
 
 

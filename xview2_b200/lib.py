@@ -78,6 +78,14 @@ _SIGNATURES = {
     "xv2_post_process": [P, P, I64, P, P, P],
     "xv2_post_process_probs": [P, P, I64, P, P, P],
     "xv2_save_probs": [P, I32, I64, I32, P, P],
+    "xv2_adaptive_avgpool_fwd": [P, P, I32, I32, I32, I32, I32, I32, P],
+    "xv2_adaptive_avgpool_bwd": [P, P, I32, I32, I32, I32, I32, I32, P],
+    "xv2_bilinear_fwd": [P, P, I32, I32, I32, I32, I32, I32, I32, P],
+    "xv2_bilinear_bwd": [P, P, I32, I32, I32, I32, I32, I32, I32, P],
+    "xv2_ordinal_loss_partials": [P, P, I64, I32, I32, P, P],
+    "xv2_ordinal_loss_finalize": [P, F, P, P, P],
+    "xv2_ordinal_loss_backward": [P, P, I64, I32, I32, P, P, P, P],
+    "xv2_ordinal_labels": [P, P, I64, I32, I32, P, P, P, P],
     "xv2_head_fwd": [P, P, P, P, I64, I32, I32, I32, P],
     "xv2_head_bwd": [P, P, P, P, P, P, I64, I32, I32, I32, P],
     "xv2_normalize_tiles": [P, P, P, I32, I32, I32, I32, P],

@@ -85,12 +85,13 @@ class UpsampleBlock(nn.Module):
 
     def __init__(self, in_channels, out_channels, skip_channels, attention, dec_interp):
         super().__init__()
-        if dec_interp:
-            raise NotImplementedError("--dec_interp (bilinear decoder, layers.py:154) is outside the accelerated path")
         self.attention = attention
         self.dec_interp = dec_interp
         self.skip_channels = skip_channels
-        self.conv_tranpose = ConvTranspose(in_channels, out_channels)  # (sic) the reference's attribute name
+        if dec_interp:  # layers.py:138-139: 3x3 conv WITH bias, then bilinear x2 (align_corners=True)
+            self.conv = conv_param(in_channels, out_channels, 3, padding=1, bias=True)
+        else:
+            self.conv_tranpose = ConvTranspose(in_channels, out_channels)  # (sic) the reference's attribute name
         self.conv_block = ConvBlock(skip_channels + out_channels, out_channels)
         if skip_channels > 0 and attention:
             att = out_channels // 2
@@ -101,7 +102,11 @@ class UpsampleBlock(nn.Module):
             self.relu = nn.ReLU(inplace=True)
 
     def forward(self, inputs, skip):
-        out = self.conv_tranpose(inputs)
+        if self.dec_interp:
+            out = run_conv(self.conv, inputs)
+            out = ops.bilinear(out, (2 * out.shape[2], 2 * out.shape[3]))
+        else:
+            out = self.conv_tranpose(inputs)
         if self.skip_channels == 0:
             return self.conv_block(out)
         if self.attention:
@@ -128,31 +133,92 @@ class FusionBlock(nn.Module):
 
 
 class OutputBlock(nn.Module):
-    """1x1 conv + bias to n_class logits (fp32).  layers.py:171-189"""
+    """1x1 conv + bias to n_class logits (fp32); CORAL head: 1-channel conv + three rank biases; --interpolate: bilinear
+    resize of the logits to 512^2 (training) / 1024^2 (eval).  layers.py:171-189"""
 
     def __init__(self, in_channels, nclass, interpolate):
         super().__init__()
-        if interpolate:
-            raise NotImplementedError("--interpolate head (layers.py:186-188) is outside the accelerated path")
-        if nclass == 3:
-            raise NotImplementedError("coral head (layers.py:175-178) is outside the accelerated path")
         self.interpolate = interpolate
-        self.coral_loss = False
-        self.conv = nn.Conv2d(in_channels, nclass, kernel_size=1)
+        self.coral_loss = nclass == 3
+        if self.coral_loss:
+            self.conv = nn.Conv2d(in_channels, 1, kernel_size=1, bias=False)
+            self.bias = nn.Parameter(torch.tensor([[[1.0]], [[0.0]], [[-1.0]]]))
+        else:
+            self.conv = nn.Conv2d(in_channels, nclass, kernel_size=1)
 
     def forward(self, inputs, second=None):
         if second is not None:  # Siamese / fused heads read cat(pre, post): tiny-N GEMM, concatenate then stream once
             inputs = torch.cat((inputs, second), 1)
-        return ops.head(inputs, self.conv.weight, self.conv.bias)
+        if self.coral_loss:  # one shared projection + per-rank bias == a 3-row head whose rows alias the same weights
+            weight, bias = self.conv.weight.expand(3, -1, -1, -1), self.bias.reshape(3)
+        else:
+            weight, bias = self.conv.weight, self.conv.bias
+        if self.interpolate:
+            # the head sits on the last ENCODER stage here (2048 / 4096 channels at 1/32 resolution): a general fp32 conv,
+            # then the bilinear resize of the logits (layers.py:186-188)
+            out = ops.conv2d(ops.cast(inputs, torch.float32), weight.contiguous(), bias)
+            size = (512, 512) if self.training else (1024, 1024)
+            return ops.bilinear(out, size)
+        return ops.head(inputs, weight, bias)
+
+
+class _PPMBranch(nn.Module):
+    """Children "1" (1x1 conv, no bias) and "2" (BatchNorm): the parameterised members of the reference's
+    nn.Sequential(AdaptiveAvgPool2d, Conv2d, BatchNorm2d, LeakyReLU) (layers.py:12-19), so the keys are features.<i>.1/2.*"""
+
+    def __init__(self, in_channels, out_channels, bins):
+        super().__init__()
+        self.bins = bins
+        self.add_module("1", conv_param(in_channels, out_channels, 1))
+        self.add_module("2", nn.BatchNorm2d(out_channels, affine=True))
+
+    def forward(self, x):
+        pooled = ops.adaptive_avg_pool2d(x, self.bins)
+        return ops.conv_bn_act(pooled, self._modules["1"], self._modules["2"], ACT_LRELU)
 
 
 class PPM(nn.Module):
+    """Pyramid pooling (layers.py:6-29): bins 1, 2, 3, 6 -> 1x1 conv -> BN -> LeakyReLU -> bilinear back to the input size,
+    concatenated with the input, 1x1 conv + bias back to in_channels."""
+
     def __init__(self, in_channels):
         super().__init__()
-        raise NotImplementedError("--ppm (layers.py:6-29) is outside the accelerated path (SURVEY.md 8f item 4)")
+        out_channels = in_channels // 4
+        self.features = nn.ModuleList([_PPMBranch(in_channels, out_channels, b) for b in (1, 2, 3, 6)])
+        self.conv = conv_param(2 * in_channels, in_channels, 1, bias=True)
+
+    def forward(self, x):
+        size = x.shape[2:]
+        outs = [x] + [ops.bilinear(f(x), size) for f in self.features]
+        return run_conv(self.conv, torch.cat(outs, 1))  # the cat is a 1/32-resolution plumbing copy
+
+
+class ASPPModule(nn.Module):
+    """conv (1x1 or dilated 3x3, no bias) -> BN -> LeakyReLU.  layers.py:32-48"""
+
+    def __init__(self, in_channels, out_channels, kernel_size, padding, dilation):
+        super().__init__()
+        self.conv = conv_param(in_channels, out_channels, kernel_size, 1, padding, dilation)
+        self.bn = nn.BatchNorm2d(out_channels, affine=True)
+        self.relu = nn.LeakyReLU(negative_slope=0.01, inplace=True)
+        torch.nn.init.kaiming_normal_(self.conv.weight)
+        _cl(self.conv)
+
+    def forward(self, x):
+        return ops.conv_bn_act(x, self.conv, self.bn, ACT_LRELU)
 
 
 class ASPP(nn.Module):
+    """Atrous spatial pyramid (layers.py:51-65): dilations 1, 3d, 6d, 9d, branches concatenated (4 x C/4 = C channels)."""
+
     def __init__(self, in_channels, dilation):
         super().__init__()
-        raise NotImplementedError("--aspp (layers.py:32-65) is outside the accelerated path (SURVEY.md 8f item 4)")
+        out_channels = in_channels // 4
+        d = [1, 3 * dilation, 6 * dilation, 9 * dilation]
+        self.aspp1 = ASPPModule(in_channels, out_channels, 1, padding=0, dilation=d[0])
+        self.aspp2 = ASPPModule(in_channels, out_channels, 3, padding=d[1], dilation=d[1])
+        self.aspp3 = ASPPModule(in_channels, out_channels, 3, padding=d[2], dilation=d[2])
+        self.aspp4 = ASPPModule(in_channels, out_channels, 3, padding=d[3], dilation=d[3])
+
+    def forward(self, x):
+        return torch.cat((self.aspp1(x), self.aspp2(x), self.aspp3(x), self.aspp4(x)), dim=1)

@@ -5,7 +5,8 @@ done in-kernel, so no boolean-mask gather and no host synchronisation happen.
 
 'ohem' reproduces what the reference actually computes: loss.py:45 slices the (values, indices) tuple returned by
 sort(), so no negative is ever discarded and the result equals the mean cross-entropy.
-'mse' and 'coral' change the head (unet.py:21-26) and are outside the accelerated path.
+'mse' and 'coral' (ordinal damage heads, unet.py:21-26, loss.py:54-65,92-94) run as their own reduction + backward kernels
+(xview2_b200/csrc/resample.cu); like the reference they are used on their own, not '+'-joined with other terms.
 """
 from torch import nn
 
@@ -21,7 +22,7 @@ class _Term(nn.Module):
         return ops.seg_loss(y_pred, y_true, self.name, post)
 
 
-losses = {name: _Term(name) for name in ("dice", "focal", "ce", "ohem")}
+losses = {name: _Term(name) for name in ("dice", "focal", "ce", "ohem", "mse", "coral")}
 
 
 class Loss(nn.Module):
@@ -29,9 +30,12 @@ class Loss(nn.Module):
         super().__init__()
         self.loss_str = args.loss_str
         self.post = args.type == "post"
-        for name in self.loss_str.split("+"):
+        names = self.loss_str.split("+")
+        for name in names:
             if name not in losses:
-                raise NotImplementedError(f"loss '{name}' is outside the accelerated path (dice, focal, ce, ohem)")
+                raise NotImplementedError(f"loss '{name}' is not one of dice, focal, ce, ohem, mse, coral")
+        if len(names) > 1 and any(n in ("mse", "coral") for n in names):
+            raise NotImplementedError("mse / coral change the head (unet.py:21-26) and cannot be '+'-joined with other terms")
         self.losses = nn.ModuleList([losses[name] for name in self.loss_str.split("+")])
 
     def forward(self, y_pred, y_true, weight=1.0, label_stride=1):

@@ -206,9 +206,12 @@ class Model(nn.Module):
 
     def save(self, preds, targets):
         """plt.py:126-144: sigmoid(pred[:, 1]) | softmax(pred) -> <results>/probs/*.npy, targets -> PNG."""
-        if self.args.type != "pre" and self.args.loss_str in ("coral", "mse"):
-            raise NotImplementedError("coral / mse heads are outside the accelerated path")
-        probs = ops.save_probs(preds).cpu().numpy()
+        if self.args.type != "pre" and self.args.loss_str == "coral":    # plt.py:129: sum(sigmoid > 0.5) + 1, int64
+            probs = ops.ordinal_labels(preds, "coral", want_u8=True).long().cpu().numpy()
+        elif self.args.type != "pre" and self.args.loss_str == "mse":    # plt.py:131: round(relu(x0)) + 1, float32, unclamped
+            probs = ops.ordinal_labels(preds, "mse", clamp4=False, want_f32=True).cpu().numpy()
+        else:
+            probs = ops.save_probs(preds).cpu().numpy()
         targets = targets.cpu().numpy().astype(np.uint8)
         from PIL import Image
         for prob, target in zip(probs, targets):
@@ -255,7 +258,7 @@ class Model(nn.Module):
          "how the pre and post images are combined for damage assessment"),
         ("encoder", str, "resnest200", ["resnest50", "resnest101", "resnest200", "resnest269", "resnet50", "resnet101", "resnet152"],
          "encoder of the U-Net"),
-        ("loss_str", str, "focal+dice", None, "'+'-joined loss terms out of dice, focal, ce, ohem (mse / coral: not accelerated)"),
+        ("loss_str", str, "focal+dice", None, "'+'-joined loss terms out of dice, focal, ce, ohem; or mse / coral alone (ordinal damage heads)"),
         ("warmup", int, 1, None, "Noam schedule: warm-up epochs"),
         ("init_lr", float, 1e-4, None, "Noam schedule: learning rate at step 0"),
         ("final_lr", float, 1e-4, None, "Noam schedule: learning rate at the last step"),
@@ -267,14 +270,14 @@ class Model(nn.Module):
     _SWITCHES = (
         ("use_scheduler", "step the Noam learning-rate schedule"),
         ("tta", "average the logits over the four flips at evaluation"),
-        ("ppm", "pyramid pooling module (not accelerated)"),
-        ("aspp", "atrous spatial pyramid pooling (not accelerated)"),
+        ("ppm", "pyramid pooling module on the last encoder stage"),
+        ("aspp", "atrous spatial pyramid pooling on the last encoder stage"),
         ("no_skip", "decoder without skip connections"),
         ("deep_supervision", "auxiliary heads on the two coarser decoder stages"),
         ("attention", "attention gates on the skip connections"),
         ("autoaugment", "ImageNet auto-augment policy (not accelerated)"),
-        ("interpolate", "bilinear head on the encoder output instead of a decoder (not accelerated)"),
-        ("dec_interp", "bilinear up-sampling in the decoder (not accelerated)"),
+        ("interpolate", "bilinear head on the encoder output instead of a decoder"),
+        ("dec_interp", "3x3 conv + bilinear up-sampling instead of the transposed conv in the decoder"),
     )
 
     @classmethod

@@ -89,21 +89,28 @@ class UNetTemplate(nn.Module):
         elif self.use_aspp:
             self.aspp = ASPP(self.enc_chn[-1], self.dilation)
         self.dec_chn = None
-        if self.interpolate:
-            raise NotImplementedError("--interpolate is outside the accelerated path (SURVEY.md 8f item 4)")
-        self.dec_chn, self.dec_l1, self.dec_l2, self.dec_l3, self.dec_l4, self.dec_l5 = get_decoder(
-            self.enc_chn, self.dilation, args.attention, self.no_skip, args.dec_interp)
+        if not self.interpolate:
+            self.dec_chn, self.dec_l1, self.dec_l2, self.dec_l3, self.dec_l4, self.dec_l5 = get_decoder(
+                self.enc_chn, self.dilation, args.attention, self.no_skip, args.dec_interp)
 
     def encode(self, data):
         enc1 = self.enc_l1(data)
         enc2 = self.enc_l2(enc1)
         enc3 = self.enc_l3(enc2)
         enc4 = self.enc_l4(enc3)
-        return [enc1, enc2, enc3, enc4, self.enc_l5(enc4)]
+        enc5 = self.enc_l5(enc4)
+        if self.use_ppm:      # unet.py:144-147
+            enc5 = self.ppm(enc5)
+        elif self.use_aspp:
+            enc5 = self.aspp(enc5)
+        return [enc1, enc2, enc3, enc4, enc5]
 
     def forward(self, data):
+        encs = self.encode(data)
+        if self.interpolate:  # unet.py:148-149: the head works on the last encoder stage
+            return encs[4], None, None
         stages = [self.dec_l1, self.dec_l2, self.dec_l3, self.dec_l4, self.dec_l5]
-        return _decode(stages, self.encode(data), self.dilation, self.no_skip)
+        return _decode(stages, encs, self.dilation, self.no_skip)
 
 
 class OutputTemplate(nn.Module):
@@ -111,7 +118,12 @@ class OutputTemplate(nn.Module):
         super().__init__()
         self.deep_supervision = deep_supervision
         self.interp = interp
-        d3, d4, d5 = scale * dec_chn[-3], scale * dec_chn[-2], scale * dec_chn[-1]
+        if self.interp:  # unet.py:180-182
+            d3 = d4 = None
+            d5 = enc_last * scale
+            self.deep_supervision = False
+        else:
+            d3, d4, d5 = scale * dec_chn[-3], scale * dec_chn[-2], scale * dec_chn[-1]
         if self.deep_supervision:
             self.output_block_ds3 = OutputBlock(d3, n_class, interp)
             self.output_block_ds4 = OutputBlock(d4, n_class, interp)
@@ -186,7 +198,12 @@ class SiameseEncUNet(_Net, _TwinEncoderMixin):
         e2 = self.enc_l2(e1)
         e3 = self.enc_l3(e2)
         e4 = self.enc_l4(e3)
-        return [e1, e2, e3, e4, self.enc_l5(e4)]
+        e5 = self.enc_l5(e4)
+        if self.use_ppm:
+            e5 = self.ppm(e5)
+        elif self.use_aspp:
+            e5 = self.aspp(e5)
+        return [e1, e2, e3, e4, e5]
 
     def forward(self, data):
         data = self._prep(data)
@@ -289,15 +306,21 @@ class ParallelEncUNet(_Net, _TwinEncoderMixin):
         self.compute_dtype = compute_dtype(args)
         self.use_ppm, self.use_aspp = args.ppm, args.aspp
         self.dilation, self.no_skip, self.interpolate = args.dilation, args.no_skip, args.interpolate
-        if self.interpolate or self.use_ppm or self.use_aspp:
-            raise NotImplementedError("--interpolate/--ppm/--aspp are outside the accelerated path")
         self.enc_chn, self.enc_l1_pre, self.enc_l2_pre, self.enc_l3_pre, self.enc_l4_pre, self.enc_l5_pre = get_encoder(
             args.encoder, self.dilation)
         _, self.enc_l1_post, self.enc_l2_post, self.enc_l3_post, self.enc_l4_post, self.enc_l5_post = get_encoder(
             args.encoder, self.dilation)
+        if self.use_ppm:
+            self.ppm_pre = PPM(self.enc_chn[-1])
+            self.ppm_post = PPM(self.enc_chn[-1])
+        elif self.use_aspp:
+            self.aspp_pre = ASPP(self.enc_chn[-1], self.dilation)
+            self.aspp_post = ASPP(self.enc_chn[-1], self.dilation)
+        self.dec_chn = None
         self.enc_chn = [2 * c for c in self.enc_chn]
-        self.dec_chn, self.dec_l1, self.dec_l2, self.dec_l3, self.dec_l4, self.dec_l5 = get_decoder(
-            self.enc_chn, self.dilation, args.attention, self.no_skip, args.dec_interp)
+        if not self.interpolate:
+            self.dec_chn, self.dec_l1, self.dec_l2, self.dec_l3, self.dec_l4, self.dec_l5 = get_decoder(
+                self.enc_chn, self.dilation, args.attention, self.no_skip, args.dec_interp)
         self.output_block = OutputTemplate(n_class, args.deep_supervision, self.dec_chn, 1, args.interpolate, self.enc_chn[-1])
 
     def forward_enc(self, data, pre):
@@ -310,7 +333,14 @@ class ParallelEncUNet(_Net, _TwinEncoderMixin):
 
     def forward(self, data):
         data = self._prep(data)
-        return self.output_block(*self._decode_cat(self.forward_enc(data[:, :3], True), self.forward_enc(data[:, 3:], False)))
+        pre, post = self.forward_enc(data[:, :3], True), self.forward_enc(data[:, 3:], False)
+        if self.use_ppm:
+            pre[4], post[4] = self.ppm_pre(pre[4]), self.ppm_post(post[4])
+        elif self.use_aspp:
+            pre[4], post[4] = self.aspp_pre(pre[4]), self.aspp_post(post[4])
+        if self.interpolate:
+            return self.output_block(pre[4], None, None, post[4])
+        return self.output_block(*self._decode_cat(pre, post))
 
 
 class DiffUNet(nn.Module):

@@ -654,6 +654,59 @@ def avg_pool2d(x, k, stride, pad=0, ceil_mode=False, count_include_pad=True):
     return _AvgPool.apply(x, k, stride, pad, ceil_mode, count_include_pad)
 
 
+class _AdaptiveAvgPool(torch.autograd.Function):
+    """nn.AdaptiveAvgPool2d(bins) (PPM, layers.py:12-21)."""
+
+    @staticmethod
+    def forward(ctx, x, bins):
+        _require_cuda(x)
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_act(n, c, bins, bins, x.dtype, x.device)
+        call("xv2_adaptive_avgpool_fwd", ptr(x), ptr(y), n, h, w, c, bins, dtype_code(x))
+        ctx.cfg = (n, c, h, w, bins)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, bins = ctx.cfg
+        dy = nhwc(dy)
+        dx = empty_act(n, c, h, w, dy.dtype, dy.device)
+        call("xv2_adaptive_avgpool_bwd", ptr(dy), ptr(dx), n, h, w, c, bins, dtype_code(dy))
+        return dx, None
+
+
+def adaptive_avg_pool2d(x, bins):
+    return _AdaptiveAvgPool.apply(x, bins)
+
+
+class _Bilinear(torch.autograd.Function):
+    """F.interpolate(mode="bilinear", align_corners=True) (layers.py:27,154,188)."""
+
+    @staticmethod
+    def forward(ctx, x, oh, ow):
+        _require_cuda(x)
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_act(n, c, oh, ow, x.dtype, x.device)
+        call("xv2_bilinear_fwd", ptr(x), ptr(y), n, h, w, c, oh, ow, dtype_code(x))
+        ctx.cfg = (n, c, h, w, oh, ow)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, oh, ow = ctx.cfg
+        dy = nhwc(dy)
+        acc = torch.zeros((n, c, h, w), dtype=torch.float32, device=dy.device).contiguous(memory_format=CL)
+        call("xv2_bilinear_bwd", ptr(dy), ptr(acc), n, h, w, c, oh, ow, dtype_code(dy))
+        return (acc if dy.dtype == torch.float32 else cast(acc, dy.dtype)), None, None
+
+
+def bilinear(x, size):
+    oh, ow = (size, size) if isinstance(size, int) else size
+    return _Bilinear.apply(x, int(oh), int(ow))
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # split attention (ResNeSt SplAtConv2d tail: radix-sum -> GAP -> fc1 -> bn1 -> relu -> fc2 -> r-softmax -> combine)
 # ---------------------------------------------------------------------------------------------------------------
@@ -928,6 +981,8 @@ _LOSS_BITS = {"dice": lib.LOSS_DICE, "focal": lib.LOSS_FOCAL, "ce": lib.LOSS_CE,
 
 def seg_loss(logits, labels, loss_str, post, weight=1.0, lstride=1):
     """Loss.forward (loss.py:85-101) for the dice / focal / ce / ohem terms.  'ce+ohem' counts CE twice like the reference."""
+    if loss_str in ORDINAL_MODE:  # single-term ordinal heads (Loss.forward applies them alone, loss.py:92-101)
+        return _OrdinalLoss.apply(logits, labels, ORDINAL_MODE[loss_str], post, weight, lstride)
     total = None
     fused = 0
     extra_ce = 0
@@ -942,6 +997,54 @@ def seg_loss(logits, labels, loss_str, post, weight=1.0, lstride=1):
     for _ in range(extra_ce):
         total = total + _SegLoss.apply(logits, labels, lib.LOSS_CE, post, weight, lstride)
     return total
+
+
+class _OrdinalLoss(torch.autograd.Function):
+    """'mse' (mode 0, loss.py:92-94) / 'coral' (mode 1, loss.py:54-65) with the `post` masking of loss.py:86-90."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, mode, post, weight, lstride):
+        _require_cuda(logits)
+        logits = nhwc(logits.float())
+        n, nl, h, w = logits.shape
+        assert nl == (1 if mode == 0 else 3), "mse expects 1 logit per pixel, coral 3"
+        if lstride != 1:
+            labels = labels[:, ::lstride, ::lstride]
+        labels = labels.contiguous()
+        assert labels.dtype == torch.uint8 and labels.shape == (n, h, w)
+        dev = logits.device
+        sums = torch.zeros(2, dtype=torch.float64, device=dev)
+        call("xv2_ordinal_loss_partials", ptr(logits), ptr(labels), n * h * w, mode, int(post), ptr(sums))
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        coef = torch.empty(1, dtype=torch.float32, device=dev)
+        call("xv2_ordinal_loss_finalize", ptr(sums), float(weight), ptr(loss), ptr(coef))
+        ctx.save_for_backward(logits, labels, coef)
+        ctx.cfg = (mode, int(post))
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, labels, coef = ctx.saved_tensors
+        mode, post = ctx.cfg
+        dl = torch.empty_like(logits)
+        up = dloss.reshape(1).float().contiguous()
+        call("xv2_ordinal_loss_backward", ptr(logits), ptr(labels), logits.shape[0] * logits.shape[2] * logits.shape[3], mode,
+             post, ptr(coef), ptr(up), ptr(dl))
+        return dl, None, None, None, None, None
+
+
+ORDINAL_MODE = {"mse": 0, "coral": 1}
+
+
+def ordinal_labels(logits, loss_str, labels=None, counters=None, clamp4=True, want_u8=False, want_f32=False):
+    """convert_to_labels (utils/f1.py:7-15) for the mse / coral heads; optionally accumulates the F1 counters."""
+    logits = nhwc(logits.detach().float())
+    n, _, h, w = logits.shape
+    u8 = torch.empty((n, h, w), dtype=torch.uint8, device=logits.device) if want_u8 else None
+    f32 = torch.empty((n, h, w), dtype=torch.float32, device=logits.device) if want_f32 else None
+    call("xv2_ordinal_labels", ptr(logits), ptr(labels.contiguous()) if labels is not None else None, n * h * w,
+         ORDINAL_MODE[loss_str], int(clamp4), ptr(counters), ptr(u8), ptr(f32))
+    return u8 if want_u8 else f32
 
 
 def f1_update(logits, labels, n_class, counters, pred_map=None):

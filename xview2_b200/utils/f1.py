@@ -10,17 +10,15 @@ from .. import ops
 
 
 def convert_to_labels(loss_str, logits):
-    """f1.py:7-15 for the accelerated heads (dice / focal / ce / ohem): argmax + 1."""
+    """f1.py:7-15: argmax + 1, or the ordinal decoding of the mse / coral heads (one libxv2 pass)."""
     if loss_str in ("mse", "coral"):
-        raise NotImplementedError("mse / coral heads are outside the accelerated path")
+        return ops.ordinal_labels(logits, loss_str, want_u8=True).long()
     return torch.argmax(logits, dim=1) + 1
 
 
 class F1:
     def __init__(self, args):
         self.loss_str = args.loss_str
-        if self.loss_str in ("mse", "coral"):
-            raise NotImplementedError("mse / coral heads are outside the accelerated path")
         self.n_class = 2 if args.type == "pre" else 5
         self.counters = None  # int64 [3 * (n_class - 1)] = tp | fp | fn, created on the first update's device
 
@@ -60,6 +58,11 @@ class F1:
             self.counters = torch.zeros(3 * (self.n_class - 1), dtype=torch.int64, device=preds.device)
         elif self.counters.device != preds.device:
             self.counters = self.counters.to(preds.device)
+        if self.n_class == 5 and self.loss_str in ("mse", "coral"):
+            got = ops.ordinal_labels(preds, self.loss_str, targets, self.counters, clamp4=True, want_u8=pred_map is not None)
+            if pred_map is not None:
+                pred_map.copy_(got)
+            return
         ops.f1_update(preds, targets, self.n_class, self.counters, pred_map)
 
     def __call__(self, preds, targets):
