@@ -160,11 +160,12 @@ int xv2_bn_bwd_reduce(const void* dy, const void* x, const void* residual, int64
                       const float* scale, const float* shift, const float* mean, const float* invstd, int32_t act,
                       double* red, void* stream);
 /* backward pass 2: dx = gamma*invstd*(du - mean(du) - xhat*mean(du*xhat)) [train] or du*scale [eval: red == NULL];
- * dres (optional) = du; dgamma/dbeta (fp32 [c], written) from red. */
+ * dres (optional) = du; dgamma/dbeta (fp32 [c]) from red: written, or ADDED TO when accumulate != 0 (the parameter's own
+ * gradient slot in the flat buffer, so that no separate accumulation launch is needed). */
 int xv2_bn_bwd_apply(const void* dy, const void* x, const void* residual, void* dx, void* dres, int64_t pixels,
                      int32_t c, int32_t dtype, const float* scale, const float* shift, const float* mean,
                      const float* invstd, const float* gamma, int32_t act, const double* red, int64_t count,
-                     float* dgamma, float* dbeta, void* stream);
+                     float* dgamma, float* dbeta, int32_t accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Pooling, NHWC.  nn.MaxPool2d(3,2,1) unet.py:81; ResNeSt avd AvgPool2d(3,s,1) and avg-down AvgPool2d(s,s,ceil) unet.py:52

@@ -103,8 +103,12 @@ def test_fp32_parity(name):
             bad.append((k, rtol, e.args[0] if e.args else None))
     assert not bad, f"{len(bad)} of {checked + len(bad)} gradient digests differ: {bad[:10]}"
     sd = model.state_dict()
+    # running statistics: 1e-3, widened only by the fixture's own conditioning (the reference's fp32-vs-fp64 train-logit error:
+    # 9e-2 on the 250-layer ResNeSt-200 fused net, ~1e-5 elsewhere)
+    l32, l64 = _as_list(fx["train_logits"])[0], _as_list(fx["train_logits64"])[0]
+    rs_tol = max(1e-3, NOISE_X * rel_err(l32, l64))
     for k, dg in fx["running_digest"].items():
-        check_digest(sd[k].float(), dg, rtol=1e-3)
+        check_digest(sd[k].float(), dg, rtol=rs_tol)
 
 
 def _amp_yardstick(fx):
@@ -114,12 +118,16 @@ def _amp_yardstick(fx):
     ns = fx["ns"]
     x, _ = golden_inputs(fx)
     errs = []
+    agree = None
     for training, key in ((False, "eval_logits64"), (True, "train_logits64")):
         P = {k: v.cuda() for k, v in golden_state(fx).items()}
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             out = OF.model_forward(P, x.cuda(), training, ns)
         errs.append(max(rel_err(o.float(), r) for o, r in zip(_as_list(sub_logits(out, fx)), _as_list(fx[key]))))
-    return errs[0], errs[1]
+        if not training:
+            a, b, _ = _decisions(sub_logits(out, fx), fx[key], 0.0, ns.loss_str)
+            agree = float((a == b).float().mean())
+    return errs[0], errs[1], agree
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -137,7 +145,7 @@ def test_bf16_parity(name):
     out, loss = run_train(fx, model)
     terr = max(rel_err(o, r) for o, r in zip(_as_list(sub_logits(out, fx)), _as_list(fx["train_logits64"])))
     lerr = abs(float(loss.detach()) - fx["loss64"]) / max(1.0, abs(fx["loss64"]))
-    amp_eval, amp_train = _amp_yardstick(fx)
+    amp_eval, amp_train, amp_agree = _amp_yardstick(fx)
     bound = max(6e-2, 1.5 * amp_eval)
     # the label map of the BENCHMARKED (tcgen05) path: bit-exact wherever the reference's own decision margin exceeds twice the
     # logit tolerance (both competing logits may move by the bound), and an overall agreement floor
@@ -145,11 +153,13 @@ def test_bf16_parity(name):
     same = ours == theirs
     agree = float(same.float().mean())
     print(f"\n[bf16 {name}] eval logits {err:.4f} (torch autocast {amp_eval:.4f}) train logits {terr:.4f} "
-          f"(torch autocast {amp_train:.4f}) loss {lerr:.5f} argmax agreement {agree:.4f} "
-          f"(clear-margin pixels: {float(clear.float().mean()):.3f} of the map)")
+          f"(torch autocast {amp_train:.4f}) loss {lerr:.5f} label-map agreement {agree:.4f} (torch autocast {amp_agree:.4f}; "
+          f"clear-margin pixels: {float(clear.float().mean()):.3f} of the map)")
     assert err < bound and terr < max(6e-2, 1.5 * amp_train) and lerr < 3e-2
     assert bool(same[clear].all()), f"{int((~same[clear]).sum())} argmax mismatches outside the tie band on the bf16 path"
-    assert agree >= 0.9, f"bf16 argmax agreement {agree:.4f} below the floor"
+    # floor: what PyTorch's own bf16 autocast run of the reference network agrees with its fp64 run on this (untrained,
+    # random-weight, hence small-margin) fixture, minus 5 points
+    assert agree >= min(0.9, amp_agree - 0.05), f"bf16 label-map agreement {agree:.4f} below the floor (torch autocast: {amp_agree:.4f})"
 
 
 def test_cuda_graph_step_matches_eager():

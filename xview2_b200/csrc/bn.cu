@@ -297,12 +297,13 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const T* __restric
                                                            const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, int act,
                                                            const double* __restrict__ red, long long count,
-                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           int accumulate) {
   const int tid = threadIdx.x;
   if (blockIdx.x == 0 && red != nullptr && dgamma != nullptr) {
     for (int i = tid; i < c; i += blockDim.x) {
-      dbeta[i] = (float)red[i];
-      dgamma[i] = (float)red[c + i];
+      dbeta[i] = (accumulate ? dbeta[i] : 0.f) + (float)red[i];
+      dgamma[i] = (accumulate ? dgamma[i] : 0.f) + (float)red[c + i];
     }
   }
   const int cvi0 = tid % m.cvb, lane = tid / m.cvb;
@@ -386,7 +387,7 @@ int bn_stream_train_apply(const void* x, const void* res, void* y, int64_t pixel
                           float* coef, int act, void* stream);
 int bn_stream_bwd_apply(const void* dy, const void* x, const void* res, void* dx, void* dres, int64_t pixels, int c,
                         const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma,
-                        int act, const double* red, int64_t count, float* dgamma, float* dbeta, void* stream);
+                        int act, const double* red, int64_t count, float* dgamma, float* dbeta, int accumulate, void* stream);
 }  // namespace xv2
 
 using namespace xv2;
@@ -478,11 +479,12 @@ extern "C" int xv2_bn_bwd_reduce(const void* dy, const void* x, const void* resi
 extern "C" int xv2_bn_bwd_apply(const void* dy, const void* x, const void* residual, void* dx, void* dres,
                                 int64_t pixels, int32_t c, int32_t dtype, const float* scale, const float* shift,
                                 const float* mean, const float* invstd, const float* gamma, int32_t act,
-                                const double* red, int64_t count, float* dgamma, float* dbeta, void* stream) {
+                                const double* red, int64_t count, float* dgamma, float* dbeta, int32_t accumulate,
+                                void* stream) {
   XV2_REQUIRE(c > 0 && pixels > 0, "bn_bwd_apply: empty tensor");
   if (bn_stream_ok(pixels, c, dtype))
     return bn_stream_bwd_apply(dy, x, residual, dx, dres, pixels, c, scale, shift, mean, invstd, gamma, act, red, count, dgamma,
-                               dbeta, stream);
+                               dbeta, accumulate, stream);
   const int vec = pick_vec(c, dtype);
   RowMap m = make_rowmap(c, vec);
   int blocks = pick_blocks(pixels, m, 8);
@@ -491,7 +493,7 @@ extern "C" int xv2_bn_bwd_apply(const void* dy, const void* x, const void* resid
                                                                        (const T*)dy, (const T*)x, (const T*)residual,
                                                                        (T*)dx, (T*)dres, pixels, c, m, scale, shift,
                                                                        mean, invstd, gamma, act, red,
-                                                                       count > 0 ? count : 1, dgamma, dbeta)));
+                                                                       count > 0 ? count : 1, dgamma, dbeta, accumulate)));
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }

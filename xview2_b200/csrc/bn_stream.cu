@@ -34,6 +34,7 @@ struct BnStreamParams {
   double* red_out;            // stats: (sum, sumsq);  bwd_reduce: (sum du, sum du*xhat)
   float inv_n;
   float *dgamma, *dbeta;
+  int accumulate;             // bwd_apply: dgamma / dbeta are added to (the parameter's .grad in the flat buffer) instead of written
   // BN_APPLY with the finalize step fused (training): coefficients come from `fin_stats` instead of scale / shift
   const double* fin_stats;    // fp64 [2c] (sum, sum of squares) over fin_count values per channel, or null
   const float *fin_gamma, *fin_beta;
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(288, 2) bn_stream_kernel(const BnStreamParams 
   }
   if (MODE == BN_BWD_APPLY && blockIdx.x == 0 && p.red_in != nullptr && p.dgamma != nullptr) {
     for (int i = tid; i < p.c; i += blockDim.x) {
-      p.dbeta[i] = (float)p.red_in[i];
-      p.dgamma[i] = (float)p.red_in[p.c + i];
+      p.dbeta[i] = (p.accumulate ? p.dbeta[i] : 0.f) + (float)p.red_in[i];
+      p.dgamma[i] = (p.accumulate ? p.dgamma[i] : 0.f) + (float)p.red_in[p.c + i];
     }
   }
   __syncthreads();
@@ -366,7 +367,7 @@ int bn_stream_bwd_reduce(const void* dy, const void* x, const void* res, int64_t
 }
 int bn_stream_bwd_apply(const void* dy, const void* x, const void* res, void* dx, void* dres, int64_t pixels, int c,
                         const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma,
-                        int act, const double* red, int64_t count, float* dgamma, float* dbeta, void* stream) {
+                        int act, const double* red, int64_t count, float* dgamma, float* dbeta, int accumulate, void* stream) {
   BnStreamParams p;
   memset(&p, 0, sizeof(p));
   p.in0 = (const __nv_bfloat16*)dy;
@@ -387,6 +388,7 @@ int bn_stream_bwd_apply(const void* dy, const void* x, const void* res, void* dx
   p.inv_n = 1.0f / (float)(count > 0 ? count : 1);
   p.dgamma = dgamma;
   p.dbeta = dbeta;
+  p.accumulate = accumulate;
   return launch_stream<BN_BWD_APPLY>(p, stream);
 }
 

@@ -496,6 +496,10 @@ class _BatchNormAct(torch.autograd.Function):
             call("xv2_bn_apply", ptr(x), ptr(residual), ptr(y), pixels, c, dtype_code(x), ptr(scale), ptr(shift), act)
         ctx.save_for_backward(x, residual, gamma, coef)
         ctx.cfg = (training, act)
+        ctx.flat_grads = (None, None)
+        if all(getattr(p, "_xv2_flat", False) and p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous()
+               for p in (gamma, beta)):
+            ctx.flat_grads = (gamma.grad, beta.grad)
         return y
 
     @staticmethod
@@ -512,10 +516,17 @@ class _BatchNormAct(torch.autograd.Function):
              ptr(invstd), act, ptr(red))
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if residual is not None and ctx.needs_input_grad[1] else None
+        gg, gb = ctx.flat_grads
+        if training and gg is not None:
+            # the parameters' own gradient slots in the flat buffer (zeroed once per step): the kernel adds to them, autograd
+            # launches no accumulation kernel for gamma / beta
+            call("xv2_bn_bwd_apply", ptr(dy), ptr(x), ptr(residual), ptr(dx), ptr(dres), pixels, c, dt, ptr(scale),
+                 ptr(shift), ptr(mean), ptr(invstd), ptr(gamma), act, ptr(red), pixels, ptr(gg), ptr(gb), 1)
+            return dx, dres, None, None, None, None, None, None, None, None, None
         dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)
         call("xv2_bn_bwd_apply", ptr(dy), ptr(x), ptr(residual), ptr(dx), ptr(dres), pixels, c, dt, ptr(scale),
              ptr(shift), ptr(mean), ptr(invstd), ptr(gamma), act, ptr(red) if training else None, pixels,
-             ptr(dgb[0]) if training else None, ptr(dgb[1]) if training else None)
+             ptr(dgb[0]) if training else None, ptr(dgb[1]) if training else None, 0)
         if not training:
             dgb[1].copy_(red[:c])
             dgb[0].copy_(red[c:])
