@@ -274,6 +274,52 @@ int xv2_post_process_probs(const float* loc, const float* dmg, int64_t pixels, u
 int xv2_save_probs(const float* logits, int32_t n, int64_t hw, int32_t ncls, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * ResNeSt split attention with its BatchNorm (bn0) + ReLU folded in (call site unet.py:52): z = RAW radix-conv output, bf16
+ * [n][hw][2c]; scale / shift / mean / invstd fp32 [2c] as written by xv2_bn_finalize; the post-BN activation is never stored.
+ * XV2_EUNSUPPORTED unless c / 8 is a power of two <= 128 (the caller then runs the unfused chain).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* gap[n][c] = mean_hw (relu(bn(z_0)) + relu(bn(z_1)))  (gap is zero-filled here) */
+int xv2_splat_bn_gap(const void* z, const float* scale, const float* shift, float* gap, int32_t n, int64_t hw, int32_t c,
+                     void* stream);
+/* out[n][hw][c] = att_0 relu(bn(z_0)) + att_1 relu(bn(z_1)) */
+int xv2_splat_bn_combine(const void* z, const float* scale, const float* shift, const float* att, void* out, int32_t n,
+                         int64_t hw, int32_t c, void* stream);
+/* backward, one pass over (z, dout): part fp64 [4][n][2c] += A1 | A2 | M1 | M2 with m = [relu input > 0]:
+ * A1 = sum dout m, A2 = sum dout m z, M1 = sum m, M2 = sum m z (caller zero-fills) */
+int xv2_splat_bn_bwd_partials(const void* z, const void* dout, const float* scale, const float* shift, double* part,
+                              int32_t n, int64_t hw, int32_t c, void* stream);
+/* datt[n][2c] = sum_hw dout * relu(bn(z)) = scale * A2 + shift * A1 */
+int xv2_splat_bn_bwd_datt(const double* part, const float* scale, const float* shift, float* datt, int32_t n, int32_t c,
+                          void* stream);
+/* BatchNorm reductions of du = (att dout + dgap / hw) m from the partial sums: red fp64 [2][2c] = (sum du, sum du * xhat) (written) */
+int xv2_splat_bn_bwd_red(const double* part, const float* att, const float* dgap, const float* mean, const float* invstd,
+                         double* red, int32_t n, int64_t hw, int32_t c, void* stream);
+/* dz = gamma invstd (du - mean(du) - xhat mean(du xhat)); dgamma / dbeta [2c] written or accumulated as xv2_bn_bwd_apply */
+int xv2_splat_bn_bwd_apply(const void* z, const void* dout, const float* att, const float* dgap, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, const float* gamma, const double* red,
+                           void* dz, float* dgamma, float* dbeta, int32_t accumulate, int32_t n, int64_t hw, int32_t c,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused tail of the localisation network: the last ConvLayer's BatchNorm + LeakyReLU (layers.py:96-100) and the 1x1 head
+ * (layers.py:180-183) without materialising the full-resolution activation between them.  z = raw conv output, bf16
+ * [pixels][c], c = 32 | 64; scale/shift/mean/invstd as written by xv2_bn_finalize; ncls 1..4; logits / dlogits fp32 [pixels][ncls].
+ * XV2_EUNSUPPORTED for other shapes (the caller then runs xv2_bn_train_apply + xv2_head_fwd).
+ * ---------------------------------------------------------------------------------------------------------- */
+int xv2_bnact_head_fwd(const void* z, int64_t pixels, int32_t c, const float* scale, const float* shift, int32_t act,
+                       const float* head_w, const float* head_b, int32_t ncls, float* logits, void* stream);
+/* backward pass 1: red fp64 [2c] += (sum du, sum du*xhat) with du = (dlogits . W) * act'(.), dhead_w [ncls][c] += dlogits^T y,
+ * dhead_b [ncls] += sum dlogits (all accumulated; caller zero-fills) */
+int xv2_bnact_head_bwd_reduce(const void* z, const float* dlogits, int64_t pixels, int32_t c, const float* scale,
+                              const float* shift, const float* mean, const float* invstd, int32_t act, const float* head_w,
+                              int32_t ncls, double* red, float* dhead_w, float* dhead_b, void* stream);
+/* backward pass 2: dz = gamma*invstd*(du - mean(du) - xhat*mean(du*xhat)); dgamma / dbeta as xv2_bn_bwd_apply */
+int xv2_bnact_head_bwd_apply(const void* z, const float* dlogits, void* dz, int64_t pixels, int32_t c, const float* scale,
+                             const float* shift, const float* mean, const float* invstd, const float* gamma, int32_t act,
+                             const float* head_w, int32_t ncls, const double* red, int64_t count, float* dgamma,
+                             float* dbeta, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Optional model parts: pyramid pooling, bilinear decoders / heads, ordinal damage heads.
  * ---------------------------------------------------------------------------------------------------------- */
 /* nn.AdaptiveAvgPool2d(bins) of PPM (layers.py:12-21): y[n][bins][bins][c]; bin i covers [floor(i L/bins), ceil((i+1) L/bins)) */

@@ -134,3 +134,102 @@ def test_fusion_block_and_loss_chain():
     assert rel_err(ai.grad, ar.grad) < 1e-3 and rel_err(bi.grad, br.grad) < 1e-3
     _compare_grads(fb, P, "f.")
     _compare_grads(head, P, "h.")
+
+
+@pytest.mark.parametrize("c,ncls,hw", [(32, 2, (24, 40)), (64, 4, (16, 24)), (32, 1, (9, 16)), (64, 3, (8, 8))])
+def test_fused_bnact_head_tail(c, ncls, hw):
+    """Last ConvLayer's train-mode BatchNorm + LeakyReLU fused with the 1x1 head (csrc/fused_tail.cu) against plain PyTorch fp32
+    on the same bf16 conv output: logits, dz, BatchNorm and head parameter gradients, running statistics."""
+    import torch.nn.functional as F
+
+    from xview2_b200 import ops
+    from xview2_b200.lib import ACT_LRELU
+    g = torch.Generator().manual_seed(31)
+    z = (torch.randn(3, c, *hw, generator=g) * 1.5 + 0.3).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    z.requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(c).cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(0.5 + torch.rand(c, generator=g))
+        bn.bias.copy_(0.2 * torch.randn(c, generator=g))
+    hw_ = torch.nn.Parameter((torch.randn(ncls, c, 1, 1, generator=g) * 0.3).cuda())
+    hb_ = torch.nn.Parameter((torch.randn(ncls, generator=g) * 0.1).cuda())
+    logits = ops.bnact_head(ops.DeferredBNAct(z, None, bn, ACT_LRELU), hw_, hb_)
+    gl = torch.randn(*logits.shape, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    logits.backward(gl)
+
+    zr = z.detach().float().requires_grad_(True)
+    bnr = torch.nn.BatchNorm2d(c).cuda().train()
+    with torch.no_grad():
+        bnr.weight.copy_(bn.weight)
+        bnr.bias.copy_(bn.bias)
+    wr, br = hw_.detach().clone().requires_grad_(True), hb_.detach().clone().requires_grad_(True)
+    y = F.leaky_relu(bnr(zr), 0.01)
+    ref = F.conv2d(y, wr, br)
+    ref.backward(gl)
+
+    def rel(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+    assert logits.dtype == torch.float32 and rel(logits, ref) < 6e-3       # y is rounded to bf16 like the unfused path stores it
+    assert rel(z.grad, zr.grad) < 1e-2                                      # dz is stored in bf16
+    assert rel(bn.weight.grad, bnr.weight.grad) < 5e-3 and rel(bn.bias.grad, bnr.bias.grad) < 5e-3
+    assert rel(hw_.grad, wr.grad) < 5e-3 and rel(hb_.grad, br.grad) < 1e-4
+    assert rel(bn.running_mean, bnr.running_mean) < 1e-4 and rel(bn.running_var, bnr.running_var) < 1e-4
+    assert int(bn.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("channels,hw,n", [(64, (16, 16), 4), (128, (8, 16), 3), (512, (8, 8), 2)])
+def test_fused_bn_split_attention(channels, hw, n):
+    """SplAtConv2d with bn0 + ReLU folded into the split-attention kernels (csrc/splat_fused.cu: the 2C-channel activation is
+    never written, the BatchNorm backward reductions come from per-image partial sums) against the oracle's SplAt in fp32."""
+    from xview2_b200 import ops
+    from xview2_b200.model.encoders import SplAtConv2d, _init_resnest
+    torch.manual_seed(3)
+    mod = SplAtConv2d(channels, 1)
+    _init_resnest(mod)
+    g = torch.Generator().manual_seed(17)
+    with torch.no_grad():
+        mod.conv.weight.copy_(mod.conv.weight.to(torch.bfloat16).float())  # both sides see the same (bf16-exact) conv weights
+        for bn in (mod.bn0, mod.bn1):
+            bn.weight.copy_(0.5 + torch.rand(bn.num_features, generator=g))
+            bn.bias.copy_(0.2 * torch.randn(bn.num_features, generator=g))
+        mod.fc2.weight.mul_(0.25)
+    mod = mod.cuda().train()
+    x = torch.randn(n, channels, *hw, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    calls = []
+    orig = ops.call
+
+    def spy(fn, *a, **kw):
+        calls.append(fn)
+        return orig(fn, *a, **kw)
+    ops.call = spy
+    try:
+        out = mod(x)
+        gy = torch.randn(*out.shape, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        out.backward(gy)
+    finally:
+        ops.call = orig
+    assert "xv2_splat_bn_gap" in calls and "xv2_splat_bn_bwd_apply" in calls and "xv2_bn_train_apply" not in calls, calls
+
+    P = {"m." + k: v.detach().float().cpu().clone() for k, v in mod.state_dict().items()}
+    for k in list(P):
+        if "running_mean" in k:
+            P[k].zero_()
+        elif "running_var" in k:
+            P[k].fill_(1.0)
+        elif "num_batches" in k:
+            P[k] = torch.zeros((), dtype=torch.int64)
+    leaves = {k: v.requires_grad_(v.is_floating_point() and "running_" not in k) for k, v in P.items()}
+    xr = x.detach().float().cpu().requires_grad_(True)
+    ref = OF._splat(leaves, "m", xr, True, 1)
+    ref.backward(gy.float().cpu())
+    assert rel_err(out, ref) < 2e-2
+    assert rel_err(x.grad, xr.grad) < 3e-2
+    named = dict(mod.named_parameters())
+    for k in ("bn0.weight", "bn0.bias", "fc1.weight", "fc2.weight", "fc2.bias", "bn1.weight", "bn1.bias", "conv.weight"):
+        assert rel_err(named[k].grad, leaves["m." + k].grad) < 3e-2, k
+    sd = mod.state_dict()
+    assert rel_err(sd["bn0.running_mean"], leaves["m.bn0.running_mean"]) < 1e-2
+    assert rel_err(sd["bn0.running_var"], leaves["m.bn0.running_var"]) < 1e-2
+    assert int(sd["bn0.num_batches_tracked"]) == 1 and int(sd["bn1.num_batches_tracked"]) == 1

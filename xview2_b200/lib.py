@@ -78,6 +78,15 @@ _SIGNATURES = {
     "xv2_post_process": [P, P, I64, P, P, P],
     "xv2_post_process_probs": [P, P, I64, P, P, P],
     "xv2_save_probs": [P, I32, I64, I32, P, P],
+    "xv2_splat_bn_gap": [P, P, P, P, I32, I64, I32, P],
+    "xv2_splat_bn_combine": [P, P, P, P, P, I32, I64, I32, P],
+    "xv2_splat_bn_bwd_partials": [P, P, P, P, P, I32, I64, I32, P],
+    "xv2_splat_bn_bwd_datt": [P, P, P, P, I32, I32, P],
+    "xv2_splat_bn_bwd_red": [P, P, P, P, P, P, I32, I64, I32, P],
+    "xv2_splat_bn_bwd_apply": [P, P, P, P, P, P, P, P, P, P, P, P, P, I32, I32, I64, I32, P],
+    "xv2_bnact_head_fwd": [P, I64, I32, P, P, I32, P, P, I32, P, P],
+    "xv2_bnact_head_bwd_reduce": [P, P, I64, I32, P, P, P, P, I32, P, I32, P, P, P, P],
+    "xv2_bnact_head_bwd_apply": [P, P, P, I64, I32, P, P, P, P, P, I32, P, I32, P, I64, P, P, I32, P],
     "xv2_adaptive_avgpool_fwd": [P, P, I32, I32, I32, I32, I32, I32, P],
     "xv2_adaptive_avgpool_bwd": [P, P, I32, I32, I32, I32, I32, I32, P],
     "xv2_bilinear_fwd": [P, P, I32, I32, I32, I32, I32, I32, I32, P],

@@ -48,8 +48,7 @@ class SplAtConv2d(nn.Module):
         self.fc2 = nn.Conv2d(inter, channels * 2, 1)
 
     def forward(self, x):
-        y = ops.conv_bn_act(x, self.conv, self.bn0, ACT_RELU)
-        return ops.split_attention(y, self.fc1, self.bn1, self.fc2)
+        return ops.conv_bn_split_attention(x, self.conv, self.bn0, self.fc1, self.bn1, self.fc2)
 
 
 class SplAtBottleneck(nn.Module):

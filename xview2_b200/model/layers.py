@@ -37,8 +37,12 @@ class ConvLayer(nn.Module):
         self.batch_norm = nn.BatchNorm2d(out_channels, affine=True)
         self.lrelu = nn.LeakyReLU(negative_slope=0.01, inplace=True)  # kept for module-tree parity (no parameters)
 
-    def forward(self, inputs, second=None):
-        """`second`: optional tensor concatenated after `inputs` on channels without materialising the cat."""
+    def forward(self, inputs, second=None, defer=False):
+        """`second`: optional tensor concatenated after `inputs` on channels without materialising the cat.
+        `defer`: return the raw conv output with its BatchNorm + LeakyReLU pending (ops.DeferredBNAct) so that the output head
+        can apply them in its own pass (the full-resolution activation is then never written)."""
+        if defer:
+            return ops.conv_bn_act_deferred(inputs, self.conv, self.batch_norm, ACT_LRELU, x2=second)
         return ops.conv_bn_act(inputs, self.conv, self.batch_norm, ACT_LRELU, x2=second)
 
 
@@ -50,8 +54,8 @@ class ConvBlock(nn.Module):
         self.conv1 = ConvLayer(in_channels, out_channels)
         self.conv2 = ConvLayer(out_channels, out_channels)
 
-    def forward(self, inputs, second=None):
-        return self.conv2(self.conv1(inputs, second))
+    def forward(self, inputs, second=None, defer=False):
+        return self.conv2(self.conv1(inputs, second), defer=defer)
 
 
 class AttentionLayer(nn.Module):
@@ -101,19 +105,19 @@ class UpsampleBlock(nn.Module):
             self.sigmoid = nn.Sigmoid()
             self.relu = nn.ReLU(inplace=True)
 
-    def forward(self, inputs, skip):
+    def forward(self, inputs, skip, defer=False):
         if self.dec_interp:
             out = run_conv(self.conv, inputs)
             out = ops.bilinear(out, (2 * out.shape[2], 2 * out.shape[3]))
         else:
             out = self.conv_tranpose(inputs)
         if self.skip_channels == 0:
-            return self.conv_block(out)
+            return self.conv_block(out, defer=defer)
         if self.attention:
             # relu(conv_o(out) + conv_s(skip)): the add + relu ride on conv_s's BN apply pass
             mix = self.conv_s(skip, ACT_RELU, residual=self.conv_o(out))
             skip = ops.gate(skip, self.psi(mix))
-        return self.conv_block(out, skip)
+        return self.conv_block(out, skip, defer=defer)
 
 
 class FusionBlock(nn.Module):
@@ -147,6 +151,12 @@ class OutputBlock(nn.Module):
             self.conv = nn.Conv2d(in_channels, nclass, kernel_size=1)
 
     def forward(self, inputs, second=None):
+        if isinstance(inputs, ops.DeferredBNAct):
+            if second is None and not self.coral_loss and not self.interpolate:
+                return ops.bnact_head(inputs, self.conv.weight, self.conv.bias)
+            inputs = inputs.materialise()
+        if isinstance(second, ops.DeferredBNAct):
+            second = second.materialise()
         if second is not None:  # Siamese / fused heads read cat(pre, post): tiny-N GEMM, concatenate then stream once
             inputs = torch.cat((inputs, second), 1)
         if self.coral_loss:  # one shared projection + per-rank bias == a 3-row head whose rows alias the same weights

@@ -55,14 +55,15 @@ def get_decoder(encf, dilation, attn, no_skip=False, dec_interp=False):
     return (DEC_CHANNELS, *stages)
 
 
-def _decode(stages, encs, dilation, no_skip):
-    """Shared decoder walk (unet.py:153-170): stages = [dec_l1..dec_l5] (None when dropped), encs = [enc1..enc5]."""
+def _decode(stages, encs, dilation, no_skip, defer_tail=False):
+    """Shared decoder walk (unet.py:153-170): stages = [dec_l1..dec_l5] (None when dropped), encs = [enc1..enc5].
+    `defer_tail`: dec5 feeds nothing but the output head, so its last BatchNorm + LeakyReLU may stay pending for the head."""
     first = {1: 0, 2: 1, 4: 2}[dilation]
     x = encs[4]
     outs = {}
     for i in range(first, 5):
         skip = None if (no_skip or i == 4) else encs[3 - i]
-        x = stages[i](x, skip)
+        x = stages[i](x, skip, defer=True) if (defer_tail and i == 4) else stages[i](x, skip)
         outs[i] = x
     return outs[4], outs[3], outs[2]
 
@@ -105,12 +106,12 @@ class UNetTemplate(nn.Module):
             enc5 = self.aspp(enc5)
         return [enc1, enc2, enc3, enc4, enc5]
 
-    def forward(self, data):
+    def forward(self, data, defer_tail=False):
         encs = self.encode(data)
         if self.interpolate:  # unet.py:148-149: the head works on the last encoder stage
             return encs[4], None, None
         stages = [self.dec_l1, self.dec_l2, self.dec_l3, self.dec_l4, self.dec_l5]
-        return _decode(stages, encs, self.dilation, self.no_skip)
+        return _decode(stages, encs, self.dilation, self.no_skip, defer_tail)
 
 
 class OutputTemplate(nn.Module):
@@ -146,7 +147,8 @@ class UNetLoc(_Net):
                                            enc_last=self.unet.enc_chn[-1])
 
     def forward(self, data):
-        return self.output_block(*self.unet(self._prep(data)))
+        # dec5 is read by the output head only: its BatchNorm + LeakyReLU are applied inside the head's own pass
+        return self.output_block(*self.unet(self._prep(data), defer_tail=True))
 
 
 class SiameseUNet(_Net):

@@ -598,6 +598,95 @@ def conv_bn_act(x, conv, bn, act=ACT_NONE, x2=None, residual=None):
     return batch_norm_act(out, bn, act, residual, stats)
 
 
+def _flat_grad_pair(gamma, beta):
+    if all(getattr(p, "_xv2_flat", False) and p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous()
+           for p in (gamma, beta)):
+        return gamma.grad, beta.grad
+    return None, None
+
+
+class _BNActHead(torch.autograd.Function):
+    """Train-mode BatchNorm + activation of the LAST decoder ConvLayer fused with the 1x1 output head (layers.py:96-100 then
+    :180-183): the full-resolution activation between them is never written (xview2_b200/csrc/fused_tail.cu)."""
+
+    @staticmethod
+    def forward(ctx, z, stats, gamma, beta, running_mean, running_var, momentum, eps, act, head_w, head_b):
+        z = nhwc(z)
+        n, c, h, w = z.shape
+        pixels = n * h * w
+        dev = z.device
+        ncls = head_w.shape[0]
+        coef = torch.empty(4, c, dtype=torch.float32, device=dev)  # mean, invstd, scale, shift
+        call("xv2_bn_finalize", ptr(stats), pixels, c, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+             float(momentum), float(eps), ptr(coef[0]), ptr(coef[1]), ptr(coef[2]), ptr(coef[3]))
+        w2 = head_w.reshape(ncls, c).contiguous()
+        logits = empty_act(n, ncls, h, w, torch.float32, dev)
+        lib.note_work(0.0, 2.0 * pixels * c + 4.0 * pixels * ncls, f"bn+act+head fwd n{n} {h}x{w} c{c} ncls{ncls}")
+        call("xv2_bnact_head_fwd", ptr(z), pixels, c, ptr(coef[2]), ptr(coef[3]), act, ptr(w2), ptr(head_b), ncls, ptr(logits))
+        ctx.save_for_backward(z, gamma, coef, w2)
+        ctx.cfg = (act, head_w.shape, head_b is not None)
+        ctx.flat_grads = _flat_grad_pair(gamma, beta)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        z, gamma, coef, w2 = ctx.saved_tensors
+        act, wshape, has_bias = ctx.cfg
+        n, c, h, w = z.shape
+        pixels = n * h * w
+        ncls = w2.shape[0]
+        dev = z.device
+        dl = nhwc(dl.float())
+        red = zeros_scratch(2 * c, torch.float64, dev)
+        dhw = zeros_scratch((ncls, c), torch.float32, dev)
+        dhb = zeros_scratch(ncls, torch.float32, dev)
+        lib.note_work(0.0, 2.0 * pixels * c + 4.0 * pixels * ncls, f"bn+act+head bwd reduce n{n} {h}x{w} c{c}")
+        call("xv2_bnact_head_bwd_reduce", ptr(z), ptr(dl), pixels, c, ptr(coef[2]), ptr(coef[3]), ptr(coef[0]), ptr(coef[1]), act,
+             ptr(w2), ncls, ptr(red), ptr(dhw), ptr(dhb))
+        dz = torch.empty_like(z)
+        gg, gb = ctx.flat_grads
+        dgb = None if gg is not None else torch.empty(2, c, dtype=torch.float32, device=dev)
+        lib.note_work(0.0, 4.0 * pixels * c + 4.0 * pixels * ncls, f"bn+act+head bwd apply n{n} {h}x{w} c{c}")
+        call("xv2_bnact_head_bwd_apply", ptr(z), ptr(dl), ptr(dz), pixels, c, ptr(coef[2]), ptr(coef[3]), ptr(coef[0]), ptr(coef[1]),
+             ptr(gamma), act, ptr(w2), ncls, ptr(red), pixels, ptr(gg if gg is not None else dgb[0]),
+             ptr(gb if gb is not None else dgb[1]), 1 if gg is not None else 0)
+        return (dz, None, None if gg is not None else dgb[0], None if gg is not None else dgb[1], None, None, None, None, None,
+                dhw.clone().reshape(wshape), dhb.clone() if has_bias else None)
+
+
+class DeferredBNAct:
+    """Raw conv output `z` whose train-mode BatchNorm + activation has not been applied yet: the consumer either fuses it
+    (ops.bnact_head) or calls materialise()."""
+
+    def __init__(self, z, stats, bn, act):
+        self.z, self.stats, self.bn, self.act = z, stats, bn, act
+
+    def materialise(self):
+        return batch_norm_act(self.z, self.bn, self.act, None, self.stats)
+
+
+def conv_bn_act_deferred(x, conv, bn, act, x2=None):
+    """conv now, BatchNorm + activation later (only while the BatchNorm uses batch statistics on the bf16 path)."""
+    if not (bn.training and bn.track_running_stats and _tc_ok(x) and conv.out_channels in (32, 64)):
+        return conv_bn_act(x, conv, bn, act, x2=x2)
+    out, stats = conv2d_stats(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0], conv.groups, x2)
+    return DeferredBNAct(out, stats, bn, act)
+
+
+def bnact_head(deferred, head_w, head_b):
+    """Consumes a DeferredBNAct with the fused BatchNorm + activation + 1x1 head kernels."""
+    bn, z = deferred.bn, nhwc(deferred.z)
+    n, c, h, w = z.shape
+    stats = deferred.stats
+    if stats is None:
+        stats = zeros_scratch(2 * c, torch.float64, z.device)
+        call("xv2_bn_stats", ptr(z), n * h * w, c, dtype_code(z), ptr(stats))
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return _BNActHead.apply(z, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                            bn.momentum if bn.momentum is not None else 0.1, bn.eps, deferred.act, head_w, head_b)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # pooling
 # ---------------------------------------------------------------------------------------------------------------
@@ -815,6 +904,102 @@ class _SplitAttention(torch.autograd.Function):
         dx = torch.empty_like(x)
         call("xv2_splat_bwd_x", ptr(dout), ptr(att), ptr(dgap), ptr(dx), n, h * w, c, dtype_code(x))
         return (dx, dw1.reshape(w1.shape), db1, dgamma, dbeta, None, None, dw2.reshape(w2.shape), db2, None, None, None)
+
+
+class _BnSplitAttention(torch.autograd.Function):
+    """bn0 (batch statistics) + ReLU + the whole split-attention tail on the RAW radix-conv output z: the post-BN activation
+    is never materialised (xview2_b200/csrc/splat_fused.cu).  Same result as batch_norm_act(z, bn0, RELU) -> _SplitAttention."""
+
+    @staticmethod
+    def forward(ctx, z, stats, g0, b0, rm0, rv0, mom0, eps0, w1, b1, gamma, beta, rmean, rvar, w2, b2, training, momentum, eps):
+        z = nhwc(z)
+        n, c2, h, w = z.shape
+        c = c2 // 2
+        hw = h * w
+        inter = w1.shape[0]
+        dev = z.device
+        coef0 = torch.empty(4, c2, dtype=torch.float32, device=dev)  # mean, invstd, scale, shift of bn0
+        call("xv2_bn_finalize", ptr(stats), n * hw, c2, ptr(g0), ptr(b0), ptr(rm0), ptr(rv0), float(mom0), float(eps0),
+             ptr(coef0[0]), ptr(coef0[1]), ptr(coef0[2]), ptr(coef0[3]))
+        gap = torch.empty((n, c), dtype=torch.float32, device=dev)
+        lib.note_work(0.0, 2.0 * n * hw * c2, f"splat bn+gap n{n} {h}x{w} c{c}")
+        call("xv2_splat_bn_gap", ptr(z), ptr(coef0[2]), ptr(coef0[3]), ptr(gap), n, hw, c)
+        w1m, w2m = w1.reshape(inter, c).contiguous(), w2.reshape(c2, inter).contiguous()
+        z1 = torch.empty((n, inter), dtype=torch.float32, device=dev)
+        a1 = torch.empty_like(z1)
+        coef = torch.empty(4, inter, dtype=torch.float32, device=dev)
+        att = torch.empty((n, c2), dtype=torch.float32, device=dev)
+        call("xv2_splat_fc_fwd", ptr(gap), ptr(w1m), ptr(b1), ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), float(momentum),
+             float(eps), int(bool(training)), ptr(w2m), ptr(b2), ptr(z1), ptr(a1), ptr(coef), ptr(att), n, c, inter)
+        out = empty_act(n, c, h, w, z.dtype, dev)
+        lib.note_work(0.0, 2.0 * n * hw * (c2 + c), f"splat bn+combine n{n} {h}x{w} c{c}")
+        call("xv2_splat_bn_combine", ptr(z), ptr(coef0[2]), ptr(coef0[3]), ptr(att), ptr(out), n, hw, c)
+        ctx.save_for_backward(z, att, gap, z1, a1, coef, coef0, w1, w2, gamma, g0)
+        ctx.training = training
+        ctx.flat_grads = _flat_grad_pair(g0, b0)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, att, gap, z1, a1, coef, coef0, w1, w2, gamma, g0 = ctx.saved_tensors
+        training = ctx.training
+        dout = nhwc(dout)
+        n, c2, h, w = z.shape
+        c = c2 // 2
+        hw = h * w
+        inter = w1.shape[0]
+        dev = z.device
+        part = zeros_scratch((4, n, c2), torch.float64, dev)
+        lib.note_work(0.0, 2.0 * n * hw * (c2 + c), f"splat bn bwd partials n{n} {h}x{w} c{c}")
+        call("xv2_splat_bn_bwd_partials", ptr(z), ptr(dout), ptr(coef0[2]), ptr(coef0[3]), ptr(part), n, hw, c)
+        datt = torch.empty((n, c2), dtype=torch.float32, device=dev)
+        call("xv2_splat_bn_bwd_datt", ptr(part), ptr(coef0[2]), ptr(coef0[3]), ptr(datt), n, c)
+        w2t = pack_weight(w2, 1, torch.float32)  # [inter][2c]
+        w1t = pack_weight(w1, 1, torch.float32)  # [c][inter]
+        scratch = torch.empty(n * (c2 + inter), dtype=torch.float32, device=dev)
+        dw2 = torch.empty((c2, inter), dtype=torch.float32, device=dev)
+        dw1 = torch.empty((inter, c), dtype=torch.float32, device=dev)
+        small = torch.empty(c2 + 3 * inter, dtype=torch.float32, device=dev)
+        db2, db1, dgamma, dbeta = small[:c2], small[c2:c2 + inter], small[c2 + inter:c2 + 2 * inter], small[c2 + 2 * inter:]
+        dgap = torch.empty((n, c), dtype=torch.float32, device=dev)
+        call("xv2_splat_fc_bwd", ptr(att), ptr(datt), ptr(a1), ptr(z1), ptr(coef), ptr(gamma), ptr(gap), ptr(w2t), ptr(w1t),
+             int(bool(training)), ptr(scratch), ptr(scratch[n * c2:]), ptr(dw2), ptr(db2), ptr(dw1), ptr(db1), ptr(dgamma),
+             ptr(dbeta), ptr(dgap), n, c, inter)
+        red = torch.empty(2 * c2, dtype=torch.float64, device=dev)
+        call("xv2_splat_bn_bwd_red", ptr(part), ptr(att), ptr(dgap), ptr(coef0[0]), ptr(coef0[1]), ptr(red), n, hw, c)
+        dz = torch.empty_like(z)
+        gg, gb = ctx.flat_grads
+        dgb0 = None if gg is not None else torch.empty(2, c2, dtype=torch.float32, device=dev)
+        lib.note_work(0.0, 2.0 * n * hw * (2 * c2 + c), f"splat bn bwd apply n{n} {h}x{w} c{c}")
+        call("xv2_splat_bn_bwd_apply", ptr(z), ptr(dout), ptr(att), ptr(dgap), ptr(coef0[2]), ptr(coef0[3]), ptr(coef0[0]),
+             ptr(coef0[1]), ptr(g0), ptr(red), ptr(dz), ptr(gg if gg is not None else dgb0[0]),
+             ptr(gb if gb is not None else dgb0[1]), 1 if gg is not None else 0, n, hw, c)
+        return (dz, None, None if gg is not None else dgb0[0], None if gg is not None else dgb0[1], None, None, None, None,
+                dw1.reshape(w1.shape), db1, dgamma, dbeta, None, None, dw2.reshape(w2.shape), db2, None, None, None)
+
+
+def conv_bn_split_attention(x, conv, bn0, fc1, bn1, fc2):
+    """SplAtConv2d body: radix conv -> bn0 -> ReLU -> split attention.  With batch statistics on the bf16 path the BatchNorm +
+    ReLU are folded into the split-attention kernels (the 2C-channel activation is never written); otherwise the unfused chain."""
+    n = x.shape[0]
+    c2 = conv.out_channels
+    vec = c2 // 16  # channel vectors of one radix half
+    fusable = (bn0.training and bn0.track_running_stats and bn1.training and _tc_ok(x) and c2 % 16 == 0 and vec >= 1 and
+               vec <= 128 and (vec & (vec - 1)) == 0 and 1 < n <= 32)
+    if not fusable:
+        return split_attention(conv_bn_act(x, conv, bn0, ACT_RELU), fc1, bn1, fc2)
+    z, stats = conv2d_stats(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0], conv.groups)
+    z = nhwc(z)
+    if stats is None:
+        stats = zeros_scratch(2 * c2, torch.float64, z.device)
+        call("xv2_bn_stats", ptr(z), z.shape[0] * z.shape[2] * z.shape[3], c2, dtype_code(z), ptr(stats))
+    for bn in (bn0, bn1):
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+    return _BnSplitAttention.apply(z, stats, bn0.weight, bn0.bias, bn0.running_mean, bn0.running_var,
+                                   bn0.momentum if bn0.momentum is not None else 0.1, bn0.eps, fc1.weight, fc1.bias,
+                                   bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, fc2.weight, fc2.bias, True,
+                                   bn1.momentum, bn1.eps)
 
 
 def split_attention(x, fc1, bn1, fc2):
