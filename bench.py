@@ -85,7 +85,8 @@ def workload_config(c, world):
     return {"workload": f"{c['what']}, batch {c['batch']}/GPU, {c['size']}x{c['size']}x3 synthetic {unit}, focal+dice loss, "
                         f"{step} ({c['baseline']})",
             "global_batch": c["batch"] * world,
-            "parallelism": f"dp{world}: {unit} sharded over ranks, NCCL all-reduce of the flat gradient buffer only",
+            "parallelism": f"dp{world}: {unit} sharded over ranks, NCCL all-reduce of the flat gradient buffer only "
+                           f"(per-stage buckets overlapped with backward)",
             "l2": "activations per step (tens of GB) exceed the 126 MB L2; no explicit flush needed"}
 
 
@@ -396,6 +397,8 @@ def run_ours(a):
         opt = model.configure_optimizers()
         flat = model.flat
         flat.broadcast_params(0)
+        if world > 1 and os.environ.get("XV2_NO_BUCKETS", "0") != "1":
+            flat.enable_bucketed_allreduce(model)  # per-stage NCCL all-reduces launched from backward hooks (overlap)
 
     # synthetic tiles: seeded uint8 "decoded PNG" bytes in the pinned ring; blocky labels
     ring = TileRing(B, S, S, post=c["post"], slots=2, device=dev)

@@ -370,6 +370,12 @@ int xv2_adamw(float* p, const float* g, float* m, float* v, int64_t numel, float
 /* SGD with momentum (apex FusedSGD defaults, plt.py:152): buf = momentum*buf + g (buf = g at step 1); p -= lr*buf. */
 int xv2_sgd(float* p, const float* g, float* buf, int64_t numel, float lr, float momentum, float grad_scale,
             int32_t step, void* stream);
+/* The same updates with every per-step scalar read from DEVICE memory, so that the launch can be replayed from a CUDA graph
+ * (the host refreshes the 32-byte block with one async copy per step):
+ *   adamw hyper fp32 [8] = lr, beta1, beta2, eps, weight_decay, 1 - beta1^step, sqrt(1 - beta2^step), grad_scale
+ *   sgd   hyper fp32 [4] = lr, momentum, grad_scale, first (1 on the first step) */
+int xv2_adamw_dev(float* p, const float* g, float* m, float* v, int64_t numel, const float* hyper, void* stream);
+int xv2_sgd_dev(float* p, const float* g, float* buf, int64_t numel, const float* hyper, void* stream);
 
 #ifdef __cplusplus
 }

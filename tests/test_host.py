@@ -358,6 +358,73 @@ def test_flat_gradient_allreduce_gloo_world2():
         assert g0 == float(sum(range(10)))  # SUM over ranks of disjoint tile shards = sum over all tiles
 
 
+def _bucket_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xview2_b200.optim import FlatParams
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.enc_l1 = torch.nn.Conv2d(3, 4, 3, padding=1)
+            self.enc_l2 = torch.nn.Conv2d(4, 4, 3, padding=1)
+            self.enc_l3 = torch.nn.Conv2d(4, 4, 3, padding=1)
+            self.dec_l1 = torch.nn.Conv2d(8, 4, 3, padding=1)
+            self.head = torch.nn.Conv2d(4, 2, 1)
+
+        def forward(self, x):
+            e1 = self.enc_l1(x)
+            e2 = self.enc_l2(e1)
+            e3 = self.enc_l3(e2) + self.enc_l3(e1)  # a stage visited twice (Siamese-style sharing)
+            return self.head(self.dec_l1(torch.cat((e3, e2), 1)))
+
+    torch.manual_seed(7)
+    net = Net()
+    flat = FlatParams(net)
+    nb = flat.enable_bucketed_allreduce(net, min_bytes=0)
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(2, 3, 8, 8, generator=g)
+    early = []
+    orig = flat._stage_done
+
+    def spy(b):
+        orig(b)
+        early.append((b["lo"], b["done"]))
+    flat._stage_done = spy
+    for b in flat._buckets:  # re-register with the spy
+        pass
+    flat.zero_grad()
+    net(x).sum().backward()
+    launched_in_backward = sum(1 for b in flat._buckets if b["done"])
+    local = None
+    n = flat.all_reduce_grads()
+    got = flat.grad.clone()
+    # reference: un-bucketed all-reduce of the same local gradients
+    flat.disable_bucketed_allreduce()
+    flat.zero_grad()
+    net(x).sum().backward()
+    flat.all_reduce_grads()
+    out[rank] = (nb, launched_in_backward, n, bool(torch.allclose(got, flat.grad, rtol=1e-6, atol=1e-7)), float(got.abs().sum()))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_overlaps_backward_and_matches_flat_gloo_world2():
+    """DDP-style buckets on the flat gradient buffer: per-stage collectives are launched from backward hooks (a twice-visited
+    stage only after its LAST visit), the remainder by all_reduce_grads(); the result equals one flat all-reduce."""
+    import torch.multiprocessing as mp
+
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29800 + os.getpid() % 150
+    mp.spawn(_bucket_worker, args=(2, port, out), nprocs=2, join=True)
+    assert len(out) == 2
+    for rank in range(2):
+        nb, launched, n, same, mag = out[rank]
+        assert nb >= 3 and launched >= 2 and n == 2 and same and mag > 0, out[rank]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # host steps of utils/post_process.py (connected-component vote, dilation) against the reference's own formulation
 # ---------------------------------------------------------------------------------------------------------------

@@ -262,6 +262,35 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// Same update with the per-step scalars read from DEVICE memory (h = lr, beta1, beta2, eps, wd, 1 - beta1^t, sqrt(1 - beta2^t),
+// grad scale): the launch carries no host scalar that changes between steps, so it can be replayed from a CUDA graph.
+__global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long numel, const float* __restrict__ h) {
+  const float lr = h[0], b1 = h[1], b2 = h[2], eps = h[3], wd = h[4], bc1 = h[5], bc2_sqrt = h[6], gscale = h[7];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel; i += (long long)gridDim.x * blockDim.x) {
+    float pi = p[i] * (1.f - lr * wd);
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+// h = lr, momentum, grad scale, first (1.0 on the first step)
+__global__ void sgd_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long numel,
+                               const float* __restrict__ h) {
+  const float lr = h[0], mu = h[1], gscale = h[2];
+  const bool first = h[3] != 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float b = first ? gi : mu * buf[i] + gi;
+    buf[i] = b;
+    p[i] -= lr * b;
+  }
+}
+
 // SGD with momentum (dampening 0, no nesterov): buf = mu*buf + g (buf = g on the first step); p -= lr*buf
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long numel,
                            float lr, float mu, float gscale, int first) {
@@ -416,6 +445,20 @@ extern "C" int xv2_adamw(float* p, const float* g, float* m, float* v, int64_t n
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   adamw_kernel<<<ew_blocks(numel), 256, 0, as_stream(stream)>>>(p, g, m, v, numel, lr, beta1, beta2, eps, weight_decay,
                                                                 bc1, bc2s, grad_scale);
+  XV2_LAUNCH_CHECK();
+  return XV2_OK;
+}
+
+extern "C" int xv2_adamw_dev(float* p, const float* g, float* m, float* v, int64_t numel, const float* hyper, void* stream) {
+  XV2_REQUIRE(numel > 0 && hyper, "adamw_dev: bad arguments");
+  adamw_dev_kernel<<<ew_blocks(numel), 256, 0, as_stream(stream)>>>(p, g, m, v, numel, hyper);
+  XV2_LAUNCH_CHECK();
+  return XV2_OK;
+}
+
+extern "C" int xv2_sgd_dev(float* p, const float* g, float* buf, int64_t numel, const float* hyper, void* stream) {
+  XV2_REQUIRE(numel > 0 && hyper, "sgd_dev: bad arguments");
+  sgd_dev_kernel<<<ew_blocks(numel), 256, 0, as_stream(stream)>>>(p, g, buf, numel, hyper);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }

@@ -33,6 +33,34 @@ struct TailParams {
 };
 
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ uint4 ldraw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void unpack8(const uint4& r, float* f) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <int NCLS> struct Grad {
+  float g[NCLS];
+};
+template <int NCLS> __device__ __forceinline__ Grad<NCLS> ldgrad(const float* dl, long long px) {
+  Grad<NCLS> r;
+  if constexpr (NCLS == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(dl + px * 2);
+    r.g[0] = v.x;
+    r.g[1] = v.y;
+  } else if constexpr (NCLS == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(dl + px * 4);
+    r.g[0] = v.x; r.g[1] = v.y; r.g[2] = v.z; r.g[3] = v.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) r.g[k] = dl[px * NCLS + k];
+  }
+  return r;
+}
+constexpr int kTailUnroll = 4;  // independent loads in flight per thread: these kernels are bound by memory-level parallelism
 
 template <int CV, int NCLS>
 __global__ void __launch_bounds__(256) tail_fwd_kernel(const TailParams p) {
@@ -50,11 +78,9 @@ __global__ void __launch_bounds__(256) tail_fwd_kernel(const TailParams p) {
 #pragma unroll
   for (int k = 0; k < NCLS; ++k) b[k] = p.hb ? p.hb[k] : 0.f;
   const long long stride = (long long)gridDim.x * ROWS;
-  for (long long px = (long long)blockIdx.x * ROWS + row; px < p.pixels; px += stride) {
-    Vec<__nv_bfloat16> v;
-    v.load(p.z + px * p.c + cv * 8);
+  auto emit = [&](long long px, const uint4& r, bool valid) {
     float f[8], acc[NCLS];
-    v.unpack(f);
+    unpack8(r, f);
 #pragma unroll
     for (int k = 0; k < NCLS; ++k) acc[k] = 0.f;
 #pragma unroll
@@ -68,11 +94,27 @@ __global__ void __launch_bounds__(256) tail_fwd_kernel(const TailParams p) {
 #pragma unroll
       for (int k = 0; k < NCLS; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
     }
-    if (cv == 0) {
+    if (cv == 0 && valid) {
 #pragma unroll
       for (int k = 0; k < NCLS; ++k) p.logits[px * NCLS + k] = acc[k] + b[k];
     }
+  };
+  // every thread of a block runs the same number of iterations (the bound is padded to whole blocks of rows) and every lane
+  // takes part in the shuffles; rows past the end compute on zeros and skip the store
+  const long long rows_total = (p.pixels + ROWS - 1) / ROWS * ROWS;
+  long long px = (long long)blockIdx.x * ROWS + row;
+  for (; px + (kTailUnroll - 1) * stride < rows_total; px += kTailUnroll * stride) {
+    uint4 r[kTailUnroll];
+#pragma unroll
+    for (int u = 0; u < kTailUnroll; ++u) {
+      const long long q = px + u * stride;
+      r[u] = q < p.pixels ? ldraw(p.z + q * p.c + cv * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kTailUnroll; ++u) emit(px + u * stride, r[u], px + u * stride < p.pixels);
   }
+  for (; px < rows_total; px += stride)
+    emit(px, px < p.pixels ? ldraw(p.z + px * p.c + cv * 8) : make_uint4(0, 0, 0, 0), px < p.pixels);
 }
 
 template <int CV, int NCLS>
@@ -100,16 +142,11 @@ __global__ void __launch_bounds__(256) tail_bwd_reduce_kernel(const TailParams p
 #pragma unroll
   for (int k = 0; k < NCLS; ++k) gb[k] = 0.f;
   const long long stride = (long long)gridDim.x * ROWS;
-  for (long long px = (long long)blockIdx.x * ROWS + row; px < p.pixels; px += stride) {
-    Vec<__nv_bfloat16> v;
-    v.load(p.z + px * p.c + cv * 8);
-    float g[NCLS];
-#pragma unroll
-    for (int k = 0; k < NCLS; ++k) g[k] = p.dl[px * NCLS + k];
+  auto accum = [&](const uint4& r, const Grad<NCLS>& gr) {
     float f[8];
-    v.unpack(f);
+    unpack8(r, f);
 #pragma unroll
-    for (int k = 0; k < NCLS; ++k) gb[k] += g[k];
+    for (int k = 0; k < NCLS; ++k) gb[k] += gr.g[k];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float u = fmaf(f[i], sc[i], sh[i]);
@@ -117,44 +154,62 @@ __global__ void __launch_bounds__(256) tail_bwd_reduce_kernel(const TailParams p
       float dy = 0.f;
 #pragma unroll
       for (int k = 0; k < NCLS; ++k) {
-        dy = fmaf(g[k], w[k][i], dy);
-        gw[k][i] = fmaf(g[k], y, gw[k][i]);
+        dy = fmaf(gr.g[k], w[k][i], dy);
+        gw[k][i] = fmaf(gr.g[k], y, gw[k][i]);
       }
       const float du = dy * act_grad(u, p.act);
       s1[i] += du;
       s2[i] = fmaf(du, (f[i] - mu[i]) * is[i], s2[i]);
     }
+  };
+  long long px = (long long)blockIdx.x * ROWS + row;
+  for (; px + (kTailUnroll - 1) * stride < p.pixels; px += kTailUnroll * stride) {
+    uint4 r[kTailUnroll];
+    Grad<NCLS> gr[kTailUnroll];
+#pragma unroll
+    for (int u = 0; u < kTailUnroll; ++u) {
+      r[u] = ldraw(p.z + (px + u * stride) * p.c + cv * 8);
+      gr[u] = ldgrad<NCLS>(p.dl, px + u * stride);
+    }
+#pragma unroll
+    for (int u = 0; u < kTailUnroll; ++u) accum(r[u], gr[u]);
   }
-  // block reduction over the ROWS pixel lanes that share a channel vector, then one atomic per channel per block
-  __shared__ float sm[256][9];
-  auto reduce8 = [&](const float* vals, auto&& sink) {
+  for (; px < p.pixels; px += stride) accum(ldraw(p.z + px * p.c + cv * 8), ldgrad<NCLS>(p.dl, px));
+  // block reduction over the pixel rows that share a channel vector (CV < 32: xor-shuffles inside the warp first, then all
+  // threads finish the 8 per-warp partials of every (vector, element) pair), one atomic per channel per block
+  __shared__ float sm[8 * CV][9];
+  auto reduce8 = [&](float* vals, auto&& sink) {
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sm[threadIdx.x][i] = vals[i];
-    __syncthreads();
-    if (row == 0) {
+    for (int off = CV; off < 32; off <<= 1) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        double t = 0.0;
-        for (int r = 0; r < ROWS; ++r) t += (double)sm[r * CV + cv][i];
-        sink(i, t);
-      }
+      for (int i = 0; i < 8; ++i) vals[i] += __shfl_xor_sync(0xffffffffu, vals[i], off);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < CV) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm[warp * CV + lane][i] = vals[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < CV * 8) {
+      const int v = threadIdx.x >> 3, i = threadIdx.x & 7;
+      double t = 0.0;
+#pragma unroll
+      for (int wp = 0; wp < 8; ++wp) t += (double)sm[wp * CV + v][i];
+      sink(v, i, t);
     }
   };
-  reduce8(s1, [&](int i, double t) { atomicAdd(&p.red[cv * 8 + i], t); });
-  reduce8(s2, [&](int i, double t) { atomicAdd(&p.red[p.c + cv * 8 + i], t); });
+  reduce8(s1, [&](int v, int i, double t) { atomicAdd(&p.red[v * 8 + i], t); });
+  reduce8(s2, [&](int v, int i, double t) { atomicAdd(&p.red[p.c + v * 8 + i], t); });
 #pragma unroll
-  for (int k = 0; k < NCLS; ++k) reduce8(gw[k], [&](int i, double t) { atomicAdd(&p.dhw[k * p.c + cv * 8 + i], (float)t); });
+  for (int k = 0; k < NCLS; ++k) reduce8(gw[k], [&](int v, int i, double t) { atomicAdd(&p.dhw[k * p.c + v * 8 + i], (float)t); });
   // bias gradient: only the cv == 0 thread of each pixel contributes
-  __syncthreads();
+  float gbv[8];
 #pragma unroll
-  for (int k = 0; k < NCLS; ++k) sm[threadIdx.x][k] = cv == 0 ? gb[k] : 0.f;
-  __syncthreads();
-  if (threadIdx.x < NCLS && p.dhb) {
-    double t = 0.0;
-    for (int r = 0; r < 256; ++r) t += (double)sm[r][threadIdx.x];
-    atomicAdd(&p.dhb[threadIdx.x], (float)t);
-  }
+  for (int i = 0; i < 8; ++i) gbv[i] = (i < NCLS && cv == 0) ? gb[i < NCLS ? i : 0] : 0.f;
+  if (p.dhb) reduce8(gbv, [&](int v, int i, double t) {
+    if (v == 0 && i < NCLS) atomicAdd(&p.dhb[i], (float)t);
+  });
 }
 
 template <int CV, int NCLS>
@@ -182,28 +237,36 @@ __global__ void __launch_bounds__(256) tail_bwd_apply_kernel(const TailParams p)
     for (int k = 0; k < NCLS; ++k) w[k][i] = p.hw[k * p.c + ch];
   }
   const long long stride = (long long)gridDim.x * ROWS;
-  for (long long px = (long long)blockIdx.x * ROWS + row; px < p.pixels; px += stride) {
-    Vec<__nv_bfloat16> v;
-    v.load(p.z + px * p.c + cv * 8);
-    float g[NCLS];
-#pragma unroll
-    for (int k = 0; k < NCLS; ++k) g[k] = p.dl[px * NCLS + k];
+  auto emit = [&](long long q, const uint4& r, const Grad<NCLS>& gr) {
     float f[8], o[8];
-    v.unpack(f);
+    unpack8(r, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float u = fmaf(f[i], sc[i], sh[i]);
       float dy = 0.f;
 #pragma unroll
-      for (int k = 0; k < NCLS; ++k) dy = fmaf(g[k], w[k][i], dy);
+      for (int k = 0; k < NCLS; ++k) dy = fmaf(gr.g[k], w[k][i], dy);
       const float du = dy * act_grad(u, p.act);
       const float xh = (f[i] - mu[i]) * is[i];
       o[i] = k0[i] * (du - k1[i] - xh * k2[i]);
     }
     Vec<__nv_bfloat16> ov;
     ov.pack(o);
-    ov.store(p.dz + px * p.c + cv * 8);
+    ov.store(p.dz + q * p.c + cv * 8);
+  };
+  long long px = (long long)blockIdx.x * ROWS + row;
+  for (; px + (kTailUnroll - 1) * stride < p.pixels; px += kTailUnroll * stride) {
+    uint4 r[kTailUnroll];
+    Grad<NCLS> gr[kTailUnroll];
+#pragma unroll
+    for (int u = 0; u < kTailUnroll; ++u) {
+      r[u] = ldraw(p.z + (px + u * stride) * p.c + cv * 8);
+      gr[u] = ldgrad<NCLS>(p.dl, px + u * stride);
+    }
+#pragma unroll
+    for (int u = 0; u < kTailUnroll; ++u) emit(px + u * stride, r[u], gr[u]);
   }
+  for (; px < p.pixels; px += stride) emit(px, ldraw(p.z + px * p.c + cv * 8), ldgrad<NCLS>(p.dl, px));
 }
 
 static int tail_grid(long long pixels, int rows_per_block) {

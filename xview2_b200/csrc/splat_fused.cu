@@ -33,25 +33,54 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
   v.load(p);
   v.unpack(f);
 }
+__device__ __forceinline__ uint4 ldraw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void unpack8(const uint4& r, float* f) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+constexpr int kUnroll = 4;  // independent 16-byte loads in flight per thread and operand: these kernels are bound by
+                            // memory-level parallelism (bytes in flight per SM), not by issue slots
+
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
   Vec<__nv_bfloat16> v;
   v.pack(f);
   v.store(p);
 }
 
-// sums `vals[8]` over the pixel lanes that share a channel vector; the lane-0 thread of each vector gets the totals
-__device__ __forceinline__ void lane_reduce8(float (*sm)[8], const float* vals, float* total, int cvt, int lanes, int cvi, int lane) {
+// Sums `vals[8]` over all threads of the block that own channel vector `cvi` (= tid % cvt) and hands every (vector, element)
+// total to `sink(cv, i, total)` exactly once.  Stage 1: xor-shuffles inside the warp (when several pixel lanes of a vector share
+// a warp); stage 2: shared memory, with ALL threads summing (a serial sum by one thread per vector cost as much as the streaming
+// loop of a small block).
+template <typename Sink>
+__device__ __forceinline__ void block_reduce_vec8(float (*sm)[8], float* vals, int cvt, Sink&& sink) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int rows;  // partial rows per channel vector left in shared memory
   __syncthreads();
+  if (cvt < 32) {
+    for (int off = cvt; off < 32; off <<= 1) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) sm[threadIdx.x][i] = vals[i];
-  __syncthreads();
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float t = 0.f;
-      for (int l = 0; l < lanes; ++l) t += sm[l * cvt + cvi][i];
-      total[i] = t;
+      for (int i = 0; i < 8; ++i) vals[i] += __shfl_xor_sync(0xffffffffu, vals[i], off);
     }
+    if (lane < cvt) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm[warp * cvt + lane][i] = vals[i];
+    }
+    rows = 8;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[tid][i] = vals[i];
+    rows = 256 / cvt;
+  }
+  __syncthreads();
+  for (int pair = tid; pair < cvt * 8; pair += 256) {
+    const int cv = pair >> 3, i = pair & 7;
+    float t = 0.f;
+    for (int r = 0; r < rows; ++r) t += sm[r * cvt + cv][i];
+    sink(cv, i, t);
   }
 }
 
@@ -72,12 +101,17 @@ __global__ void __launch_bounds__(256) splat_bn_gap_kernel(const __nv_bfloat16* 
   const __nv_bfloat16* zb = z + (long long)nb * hw * 2 * c + ch0;
   const long long stride = (long long)gridDim.x * m.lanes;
   long long p = (long long)blockIdx.x * m.lanes + lane;
-  for (; p + stride < hw; p += 2 * stride) {
-    float f0[8], f1[8];
-    load8(zb + p * 2 * c, f0);
-    load8(zb + (p + stride) * 2 * c, f1);
+  for (; p + (kUnroll - 1) * stride < hw; p += kUnroll * stride) {
+    uint4 r[kUnroll];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += fmaxf(fmaf(f0[i], sc[i], sh[i]), 0.f) + fmaxf(fmaf(f1[i], sc[i], sh[i]), 0.f);
+    for (int u = 0; u < kUnroll; ++u) r[u] = ldraw(zb + (p + u * stride) * 2 * c);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      float f0[8];
+      unpack8(r[u], f0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += fmaxf(fmaf(f0[i], sc[i], sh[i]), 0.f);
+    }
   }
   for (; p < hw; p += stride) {
     float f0[8];
@@ -85,13 +119,10 @@ __global__ void __launch_bounds__(256) splat_bn_gap_kernel(const __nv_bfloat16* 
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] += fmaxf(fmaf(f0[i], sc[i], sh[i]), 0.f);
   }
-  float tot[8];
-  lane_reduce8(sm, acc, tot, m.cvt, m.lanes, cvi, lane);
-  if (lane == 0) {
-    const int chg = ch0 >= c ? ch0 - c : ch0;  // both radix halves add into the same gap channel
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&gap[(long long)nb * c + chg + i], tot[i] * inv_hw);
-  }
+  block_reduce_vec8(sm, acc, m.cvt, [&](int cv, int i, float t) {
+    const int ch = cv * 8 + i;
+    atomicAdd(&gap[(long long)nb * c + (ch >= c ? ch - c : ch)], t * inv_hw);  // both radix halves add into one gap channel
+  });
 }
 
 // ---- forward 2: combine (a thread owns BOTH radix halves of its 8 channels) ---------------------------------------
@@ -113,15 +144,23 @@ __global__ void __launch_bounds__(256) splat_bn_combine_kernel(const __nv_bfloat
   const __nv_bfloat16* zb = z + (long long)nb * hw * 2 * c + ch0;
   __nv_bfloat16* ob = out + (long long)nb * hw * c + ch0;
   const long long stride = (long long)gridDim.x * m.lanes;
-  for (long long p = (long long)blockIdx.x * m.lanes + lane; p < hw; p += stride) {
+  long long p = (long long)blockIdx.x * m.lanes + lane;
+  auto emit = [&](long long px, const uint4& r0, const uint4& r1) {
     float f0[8], f1[8], o[8];
-    load8(zb + p * 2 * c, f0);
-    load8(zb + p * 2 * c + c, f1);
+    unpack8(r0, f0);
+    unpack8(r1, f1);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       o[i] = a0[i] * fmaxf(fmaf(f0[i], s0[i], h0[i]), 0.f) + a1[i] * fmaxf(fmaf(f1[i], s1[i], h1[i]), 0.f);
-    store8(ob + p * c, o);
+    store8(ob + px * c, o);
+  };
+  for (; p + stride < hw; p += 2 * stride) {
+    const uint4 r00 = ldraw(zb + p * 2 * c), r01 = ldraw(zb + p * 2 * c + c);
+    const uint4 r10 = ldraw(zb + (p + stride) * 2 * c), r11 = ldraw(zb + (p + stride) * 2 * c + c);
+    emit(p, r00, r01);
+    emit(p + stride, r10, r11);
   }
+  for (; p < hw; p += stride) emit(p, ldraw(zb + p * 2 * c), ldraw(zb + p * 2 * c + c));
 }
 
 // ---- backward 1: per-image partial sums -------------------------------------------------------------------------
@@ -145,10 +184,10 @@ __global__ void __launch_bounds__(256) splat_bn_bwd_partials_kernel(const __nv_b
   const __nv_bfloat16* zb = z + (long long)nb * hw * 2 * c + ch0;
   const __nv_bfloat16* db = dout + (long long)nb * hw * c + chd;
   const long long stride = (long long)gridDim.x * m.lanes;
-  for (long long p = (long long)blockIdx.x * m.lanes + lane; p < hw; p += stride) {
+  auto accum = [&](const uint4& rz, const uint4& rd) {
     float f[8], d[8];
-    load8(zb + p * 2 * c, f);
-    load8(db + p * c, d);
+    unpack8(rz, f);
+    unpack8(rd, d);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const bool on = fmaf(f[i], sc[i], sh[i]) > 0.f;
@@ -158,30 +197,25 @@ __global__ void __launch_bounds__(256) splat_bn_bwd_partials_kernel(const __nv_b
       m1[i] += on ? 1.f : 0.f;
       m2[i] += fm;
     }
+  };
+  long long p = (long long)blockIdx.x * m.lanes + lane;
+  for (; p + (kUnroll - 1) * stride < hw; p += kUnroll * stride) {
+    uint4 rz[kUnroll], rd[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      rz[u] = ldraw(zb + (p + u * stride) * 2 * c);
+      rd[u] = ldraw(db + (p + u * stride) * c);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) accum(rz[u], rd[u]);
   }
+  for (; p < hw; p += stride) accum(ldraw(zb + p * 2 * c), ldraw(db + p * c));
   const long long plane = (long long)n * 2 * c;
-  double* dst = part + (long long)nb * 2 * c + ch0;
-  float tot[8];
-  lane_reduce8(sm, a1, tot, m.cvt, m.lanes, cvi, lane);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(dst + i, (double)tot[i]);
-  }
-  lane_reduce8(sm, a2, tot, m.cvt, m.lanes, cvi, lane);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(dst + plane + i, (double)tot[i]);
-  }
-  lane_reduce8(sm, m1, tot, m.cvt, m.lanes, cvi, lane);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(dst + 2 * plane + i, (double)tot[i]);
-  }
-  lane_reduce8(sm, m2, tot, m.cvt, m.lanes, cvi, lane);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(dst + 3 * plane + i, (double)tot[i]);
-  }
+  double* dst = part + (long long)nb * 2 * c;
+  block_reduce_vec8(sm, a1, m.cvt, [&](int cv, int i, float t) { atomicAdd(dst + cv * 8 + i, (double)t); });
+  block_reduce_vec8(sm, a2, m.cvt, [&](int cv, int i, float t) { atomicAdd(dst + plane + cv * 8 + i, (double)t); });
+  block_reduce_vec8(sm, m1, m.cvt, [&](int cv, int i, float t) { atomicAdd(dst + 2 * plane + cv * 8 + i, (double)t); });
+  block_reduce_vec8(sm, m2, m.cvt, [&](int cv, int i, float t) { atomicAdd(dst + 3 * plane + cv * 8 + i, (double)t); });
 }
 
 // datt[n][2c] = scale * A2 + shift * A1
@@ -254,18 +288,30 @@ __global__ void __launch_bounds__(256) splat_bn_bwd_apply_kernel(const __nv_bflo
   const __nv_bfloat16* db = dout + (long long)nb * hw * c + chd;
   __nv_bfloat16* ob = dz + (long long)nb * hw * c2 + ch0;
   const long long stride = (long long)gridDim.x * m.lanes;
-  for (long long p = (long long)blockIdx.x * m.lanes + lane; p < hw; p += stride) {
+  auto emit = [&](long long px, const uint4& rz, const uint4& rd) {
     float f[8], d[8], o[8];
-    load8(zb + p * c2, f);
-    load8(db + p * c, d);
+    unpack8(rz, f);
+    unpack8(rd, d);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float du = fmaf(f[i], sc[i], sh[i]) > 0.f ? fmaf(a[i], d[i], g[i]) : 0.f;
       const float xh = (f[i] - mu[i]) * is[i];
       o[i] = k0[i] * (du - k1[i] - xh * k2[i]);
     }
-    store8(ob + p * c2, o);
+    store8(ob + px * c2, o);
+  };
+  long long p = (long long)blockIdx.x * m.lanes + lane;
+  for (; p + (kUnroll - 1) * stride < hw; p += kUnroll * stride) {
+    uint4 rz[kUnroll], rd[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      rz[u] = ldraw(zb + (p + u * stride) * c2);
+      rd[u] = ldraw(db + (p + u * stride) * c);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) emit(p + u * stride, rz[u], rd[u]);
   }
+  for (; p < hw; p += stride) emit(p, ldraw(zb + p * c2), ldraw(db + p * c));
 }
 
 static bool splat_map(int vectors, SplatMap* m) {
@@ -276,7 +322,7 @@ static bool splat_map(int vectors, SplatMap* m) {
 }
 static dim3 splat_grid(int n, long long hw, int lanes, int per_lane) {
   long long bx = cdiv(hw, (long long)lanes * per_lane);
-  long long cap = cdiv(8LL * kNumSMs, n);
+  long long cap = cdiv(4LL * kNumSMs, n);
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   return dim3((unsigned)bx, (unsigned)n);

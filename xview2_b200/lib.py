@@ -100,6 +100,8 @@ _SIGNATURES = {
     "xv2_normalize_tiles": [P, P, P, I32, I32, I32, I32, P],
     "xv2_adamw": [P, P, P, P, I64, F, F, F, F, F, I32, F, P],
     "xv2_sgd": [P, P, P, I64, F, F, F, I32, P],
+    "xv2_adamw_dev": [P, P, P, P, I64, P, P],
+    "xv2_sgd_dev": [P, P, P, I64, P, P],
 }
 
 _lib = None

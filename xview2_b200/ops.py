@@ -12,6 +12,12 @@ CL = torch.channels_last
 
 # Set to False to force the SIMT path everywhere (used by tests to cross-check the tensor-core kernels).
 USE_TENSOR_CORES = True
+# Fused streaming paths (A/B switches for tests and profiling; XV2_NO_FUSE=1 turns both off):
+#   FUSE_SPLAT_BN: bn0 + ReLU folded into the split-attention kernels (csrc/splat_fused.cu)
+#   FUSE_TAIL    : last decoder BatchNorm + LeakyReLU folded into the 1x1 head (csrc/fused_tail.cu)
+import os as _os0
+FUSE_SPLAT_BN = _os0.environ.get("XV2_NO_FUSE", "0") != "1"
+FUSE_TAIL = _os0.environ.get("XV2_NO_FUSE", "0") != "1"
 
 
 def nhwc(t):
@@ -667,7 +673,7 @@ class DeferredBNAct:
 
 def conv_bn_act_deferred(x, conv, bn, act, x2=None):
     """conv now, BatchNorm + activation later (only while the BatchNorm uses batch statistics on the bf16 path)."""
-    if not (bn.training and bn.track_running_stats and _tc_ok(x) and conv.out_channels in (32, 64)):
+    if not (FUSE_TAIL and bn.training and bn.track_running_stats and _tc_ok(x) and conv.out_channels in (32, 64)):
         return conv_bn_act(x, conv, bn, act, x2=x2)
     out, stats = conv2d_stats(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0], conv.groups, x2)
     return DeferredBNAct(out, stats, bn, act)
@@ -984,7 +990,7 @@ def conv_bn_split_attention(x, conv, bn0, fc1, bn1, fc2):
     n = x.shape[0]
     c2 = conv.out_channels
     vec = c2 // 16  # channel vectors of one radix half
-    fusable = (bn0.training and bn0.track_running_stats and bn1.training and _tc_ok(x) and c2 % 16 == 0 and vec >= 1 and
+    fusable = (FUSE_SPLAT_BN and bn0.training and bn0.track_running_stats and bn1.training and _tc_ok(x) and c2 % 16 == 0 and vec >= 1 and
                vec <= 128 and (vec & (vec - 1)) == 0 and 1 < n <= 32)
     if not fusable:
         return split_attention(conv_bn_act(x, conv, bn0, ACT_RELU), fc1, bn1, fc2)

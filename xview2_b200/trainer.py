@@ -143,6 +143,8 @@ class Trainer:
         optimizer, scheduler = (conf["optimizer"], conf["lr_scheduler"]["scheduler"]) if isinstance(conf, dict) else (conf, None)
         flat = model.flat
         flat.broadcast_params(0)
+        if self.world_size > 1:
+            flat.enable_bucketed_allreduce(model)  # DDP-style overlap of the gradient all-reduce with backward (main.py:106-107)
         from . import ops
         ops.enable_wgrad_side_stream(True)  # step()/all_reduce_grads()/zero_grad() below are the sync points
         self.scheduler = scheduler
