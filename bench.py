@@ -635,7 +635,14 @@ def run_ours(a):
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # The captured CUDA graph holds NCCL work: tearing the process group down underneath it can block in NCCL's watchdog.
+        # Every rank has passed the final fence and rank 0 has printed, so leave without the teardown.
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

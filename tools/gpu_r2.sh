@@ -27,8 +27,8 @@ for s in $STAGES; do
         --kernel-id :::1\|2 -f -o gpurun_out/prof_full python tools/layer_profile.py --ncu > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log
         $NCU -i gpurun_out/prof_full.ncu-rep --page raw --csv > gpurun_out/prof_full_raw.csv 2>/dev/null; wc -l gpurun_out/prof_full_raw.csv ;;
     scale2|scale4|scale8) n=${s#scale}; for c in ${CFGS:-c2}; do
-        timeout 1500 $TR --nproc-per-node $n --master-port 295$n bench.py --config $c --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_${c}_n$n.json 2> gpurun_out/scale_${c}_n$n.err
-        python tools/show_bench.py gpurun_out/scale_${c}_n$n.json; tail -3 gpurun_out/scale_${c}_n$n.err; done ;;
+        timeout -k 10 ${SCALE_TIMEOUT:-240} $TR --nproc-per-node $n --master-port 295$n bench.py --config $c --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_${c}_n$n${TAG:-}.json 2> gpurun_out/scale_${c}_n$n${TAG:-}.err
+        python tools/show_bench.py gpurun_out/scale_${c}_n$n${TAG:-}.json | head -3; tail -3 gpurun_out/scale_${c}_n$n${TAG:-}.err | cut -c1-300; done ;;
     *) echo "unknown stage $s" ;;
   esac
 done
