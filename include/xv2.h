@@ -269,6 +269,17 @@ int xv2_post_process(const float* loc_logits, const float* dmg_logits, int64_t p
 int xv2_post_process_probs(const float* loc, const float* dmg, int64_t pixels, uint8_t* pre_map, uint8_t* post_map,
                            void* stream);
 
+/* Connected-component majority vote (utils/post_process.py:39-43): every 4-connected component of post > 0 takes its most
+ * frequent class (1..4; ties -> smallest).  post / out uint8 [n][h][w]; labels int32 [n*h*w] and votes int32 [n*h*w][4] scratch. */
+int xv2_cc_majority_vote(const uint8_t* post, uint8_t* out, int32_t* labels, int32_t* votes, int32_t n, int32_t h, int32_t w,
+                         void* stream);
+/* Grey-scale dilation with a k x k square footprint, k odd (post_process.py:44-45: skimage dilation(img, square(k))) */
+int xv2_dilate_square(const uint8_t* in, uint8_t* out, int32_t n, int32_t h, int32_t w, int32_t k, void* stream);
+/* xView2 scorer counters (utils/xview2_metrics.py:61-92), accumulated: counters int64 [15] = lTP lFN lFP, then (TP FN FP) of
+ * damage classes 1..4 on target-building pixels with the damage prediction masked by the predicted buildings */
+int xv2_score_counts(const uint8_t* loc_pred, const uint8_t* dmg_pred, const uint8_t* loc_targ, const uint8_t* dmg_targ,
+                     int64_t pixels, int64_t* counters, void* stream);
+
 /* Model.save (plt.py:126-131): probabilities in the layout the reference writes per tile with np.save:
  * ncls 2: out[n][hw] = sigmoid(logit[..,1]);  ncls 4: out[n][4][hw] = softmax (planar). */
 int xv2_save_probs(const float* logits, int32_t n, int64_t hw, int32_t ncls, float* out, void* stream);
@@ -362,6 +373,23 @@ int xv2_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, 
  * ---------------------------------------------------------------------------------------------------------- */
 int xv2_normalize_tiles(const uint8_t* pre, const uint8_t* post, void* out, int32_t n, int32_t h, int32_t w,
                         int32_t out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Train-time augmentation on the device (pytorch_loader.py:57-63,73-92,109-115,124-148): RandomScale (cubic / nearest) ->
+ * CropNonEmptyMaskIfExists -> H / V flip -> GaussNoise -> RandomBrightnessContrast -> Normalize, as ONE gather kernel.
+ * params fp32 [n][16] per sample (host-drawn decisions):
+ *   0 src_w/scaled_w  1 src_h/scaled_h  2 scaled_w  3 scaled_h  4 crop x0  5 crop y0  6 flip_h  7 flip_v  8 sigma(pre)  9 sigma(post)
+ *   10 alpha(pre)  11 beta(pre)  12 alpha(post)  13 beta(post)  14 noise seed  15 zoom on
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Crop origin (x0, y0) in the SCALED mask: the floor(u0 * count)-th non-zero pixel minus floor(u1 * cw), floor(u2 * ch), clipped;
+ * an empty mask gives a uniform origin.  uniforms fp32 [n][3] in [0,1); rowcount int32 [n][max_rows] scratch; origin int32 [n][2]. */
+int xv2_crop_origin(const uint8_t* mask, const float* params, const float* uniforms, int32_t* rowcount, int32_t* origin,
+                    int32_t n, int32_t sh, int32_t sw, int32_t max_rows, int32_t ch, int32_t cw, void* stream);
+/* pre / post uint8 [n][sh][sw][3] (post optional), mask uint8 [n][sh][sw]; origin int32 [n][2] (null: params 4,5);
+ * out [n][oh][ow][3|6] normalised (out_dtype) and / or out_u8 (the augmented bytes before Normalize); mask_out uint8 [n][oh][ow]. */
+int xv2_augment_tiles(const uint8_t* pre, const uint8_t* post, const uint8_t* mask, const float* params, const int32_t* origin,
+                      void* out, uint8_t* out_u8, uint8_t* mask_out, int32_t n, int32_t sh, int32_t sw, int32_t oh, int32_t ow,
+                      int32_t out_dtype, void* stream);
 
 /* Fused AdamW over one flat parameter buffer (torch.optim.AdamW semantics, plt.py:154): step is 1-based; the gradient
  * is multiplied by grad_scale first (1/world_size after the SUM all-reduce of the data-parallel ranks). */

@@ -581,3 +581,125 @@ def deterministic_state(shapes, seed=1):
             t = t * 0.25
         out[key] = t.to(dtype)
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# train-time augmentation (pytorch_loader.py:57-63,73-92,109-115,124-148), restated per OUTPUT pixel in float32 exactly as the
+# device kernel evaluates it (xview2_b200/csrc/augment.cu); cv2 / albumentations semantics are cited inline
+# --------------------------------------------------------------------------------------------------------------
+def _hash32(x):
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    x *= np.uint32(0x7feb352d)
+    x ^= x >> np.uint32(15)
+    x *= np.uint32(0x846ca68b)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def counter_normal(seed, idx):
+    """N(0, 1) from a counter: Box-Muller on two hashed 24-bit uniforms (float32)."""
+    idx = idx.astype(np.uint32)
+    seed = np.uint32(seed)
+    with np.errstate(over="ignore"):
+        a = _hash32(idx * np.uint32(2) + np.uint32(0x9e3779b9) * seed)
+        b = _hash32(idx * np.uint32(2) + np.uint32(1) + np.uint32(0x85ebca6b) * seed)
+    u1 = ((a >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * np.float32(1.0 / 16777216.0)
+    u2 = (b >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return np.sqrt(np.float32(-2.0) * np.log(u1)) * np.cos(np.float32(6.28318530717958647692) * u2)
+
+
+def _cubic_weights(t):
+    """Keys cubic, A = -0.75 (cv2 INTER_CUBIC), float32, same operation order as the device kernel."""
+    A = np.float32(-0.75)
+    t = t.astype(np.float32)
+    t1, u = t + np.float32(1), np.float32(1) - t
+    w0 = ((A * t1 + np.float32(3.75)) * t1 + np.float32(-6.0)) * t1 + np.float32(3.0)
+    w1 = ((np.float32(1.25) * t + np.float32(-2.25)) * t) * t + np.float32(1)
+    w2 = ((np.float32(1.25) * u + np.float32(-2.25)) * u) * u + np.float32(1)
+    w3 = ((np.float32(1) - w0) - w1) - w2
+    return [w0, w1, w2, w3]
+
+
+def augment_restatement(pre, post, mask, P, origin, crop=512):
+    """One sample.  pre / post: uint8 (H, W, 3) (post may be None), mask uint8 (H, W), P: the 16 host-drawn floats of
+    include/xv2.h, origin (x0, y0) in the scaled image.  Returns (uint8 (crop, crop, 3|6) augmented bytes, float32 normalised
+    (crop, crop, 3|6), uint8 (crop, crop) mask).
+
+    RandomScale: cv2.resize(dsize) -> scale = src / dst, cubic fx = (dx + .5) scale - .5 with replicated borders, nearest
+    sx = min(floor(dx scale), src - 1) (pytorch_loader.py:58,110); CropNonEmptyMaskIfExists / flips are index arithmetic
+    (:57,59-60); GaussNoise: clip(img + N(0, var)) truncated to uint8 per image (:61, intensity_aug :45-51);
+    RandomBrightnessContrast: LUT clip(x alpha + beta 255) (:62); Normalize (:63)."""
+    P = np.asarray(P, np.float32)
+    sh, sw = mask.shape
+    x0, y0 = int(origin[0]), int(origin[1])
+    ys, xs = np.meshgrid(np.arange(crop), np.arange(crop), indexing="ij")
+    xc = (crop - 1 - xs if P[6] != 0 else xs) + x0
+    yc = (crop - 1 - ys if P[7] != 0 else ys) + y0
+    zoom = P[15] != 0
+    ifx, ify = sw / float(int(P[2])), sh / float(int(P[3]))  # cv2: double scale from the integer sizes
+    if zoom:
+        mx = np.minimum(np.floor(xc.astype(np.float64) * ifx).astype(np.int64), sw - 1)
+        my = np.minimum(np.floor(yc.astype(np.float64) * ify).astype(np.int64), sh - 1)
+    else:
+        mx, my = xc, yc
+    mask_out = mask[my, mx]
+    imgs = [pre] + ([post] if post is not None else [])
+    out_u8 = np.zeros((crop, crop, 3 * len(imgs)), np.uint8)
+    if zoom:
+        fx = ((xc.astype(np.float64) + 0.5) * ifx - 0.5).astype(np.float32)
+        fy = ((yc.astype(np.float64) + 0.5) * ify - 0.5).astype(np.float32)
+        sx, sy = np.floor(fx).astype(np.int64), np.floor(fy).astype(np.int64)
+        wx, wy = _cubic_weights(fx - sx.astype(np.float32)), _cubic_weights(fy - sy.astype(np.float32))
+        ix = [np.clip(sx - 1 + k, 0, sw - 1) for k in range(4)]
+        iy = [np.clip(sy - 1 + k, 0, sh - 1) for k in range(4)]
+    pix = (ys * crop + xs).astype(np.int64)  # output pixel index within the sample (the caller adds the sample offset)
+    for im, img in enumerate(imgs):
+        sigma, alpha, beta = P[8 + im], P[10 + 2 * im], P[11 + 2 * im]
+        for ch in range(3):
+            if zoom:
+                acc = np.zeros((crop, crop), np.float32)
+                for r in range(4):
+                    row = np.zeros((crop, crop), np.float32)
+                    for k in range(4):
+                        row = row + wx[k] * img[iy[r], ix[k], ch].astype(np.float32)
+                    acc = acc + wy[r] * row
+                v = np.clip(np.rint(acc), 0, 255).astype(np.float32)
+            else:
+                v = img[yc, xc, ch].astype(np.float32)
+            if sigma > 0:
+                idx = ((pix + augment_restatement.sample_base) * 2 + im) * 3 + ch
+                v = np.floor(np.clip(v + sigma * counter_normal(int(P[14]), idx), 0, 255)).astype(np.float32)
+            if alpha != 1 or beta != 0:
+                v = np.floor(np.clip(v * alpha + beta * np.float32(255), 0, 255)).astype(np.float32)
+            out_u8[:, :, im * 3 + ch] = v.astype(np.uint8)
+    mean = np.array(IMAGENET_MEAN * len(imgs), np.float32) * np.float32(255)
+    inv = np.float32(1) / (np.array(IMAGENET_STD * len(imgs), np.float32) * np.float32(255))
+    return out_u8, (out_u8.astype(np.float32) - mean) * inv, mask_out
+
+
+augment_restatement.sample_base = 0  # index of the sample's first output pixel in the batch (i = img * crop^2 + pix on the device)
+
+
+def crop_origin_restatement(mask, P, u, crop=512):
+    """CropNonEmptyMaskIfExists.update_params (albumentations 0.5.1) on the nearest-scaled mask with the three uniforms the
+    device kernel consumes: k = floor(u0 count)-th non-zero pixel (row-major), minus floor(u1 cw) / floor(u2 ch), clipped."""
+    P = np.asarray(P, np.float32)
+    sh, sw = mask.shape
+    ws, hs = int(P[2]), int(P[3])
+    if P[15] != 0:
+        mx = np.minimum(np.floor(np.arange(ws, dtype=np.float64) * (sw / float(ws))).astype(np.int64), sw - 1)
+        my = np.minimum(np.floor(np.arange(hs, dtype=np.float64) * (sh / float(hs))).astype(np.int64), sh - 1)
+        scaled = mask[my][:, mx]
+    else:
+        scaled = mask
+    yy, xx = np.nonzero(scaled)
+    u = np.asarray(u, np.float32)
+    if len(yy):
+        k = min(int(np.floor(u[0] * np.float32(len(yy)))), len(yy) - 1)
+        px = int(np.clip(xx[k] - int(np.floor(u[1] * np.float32(crop))), 0, ws - crop))
+        py = int(np.clip(yy[k] - int(np.floor(u[2] * np.float32(crop))), 0, hs - crop))
+    else:
+        px = min(int(np.floor(u[1] * np.float32(ws - crop + 1))), ws - crop)
+        py = min(int(np.floor(u[2] * np.float32(hs - crop + 1))), hs - crop)
+    return px, py

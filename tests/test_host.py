@@ -121,10 +121,11 @@ def tile_dir(tmp_path):
     return tmp_path
 
 
-def test_datasets_return_decoded_uint8_tiles(tile_dir):
+def test_datasets_return_decoded_uint8_tiles(tile_dir, monkeypatch):
     import cv2
 
     from xview2_b200.data_loading.pytorch_loader import TestDataset, TrainPostDataset, TrainPreDataset
+    monkeypatch.setenv("XV2_HOST_AUG", "1")  # the host restatement of the augmentations (default: on the device, below)
 
     ds = TestDataset(str(tile_dir / "holdout"), "post", False)
     assert len(ds) == 3
@@ -142,6 +143,60 @@ def test_datasets_return_decoded_uint8_tiles(tile_dir):
     assert item["tiles"].shape == item["tiles_post"].shape == (512, 512, 3) and item["mask"].any()
     with pytest.raises(NotImplementedError):
         TrainPreDataset(str(tile_dir / "train"), "pre", True)
+
+
+def test_train_datasets_hand_decisions_to_the_device_augmentation(tile_dir):
+    """Default training path: full decoded tiles + 19 host-drawn floats per sample; the pixels are augmented on the GPU."""
+    from xview2_b200.data_loading.pytorch_loader import GpuTrainAugment, TrainPostDataset, TrainPreDataset
+
+    pre = TrainPreDataset(str(tile_dir / "train"), "pre", False)
+    assert pre.out_size == 1024
+    a, b = pre[1], pre[1]
+    assert a["tiles"].shape == (1024, 1024, 3) and a["mask"].shape == (1024, 1024)
+    assert a["aug"].dtype == np.float32 and a["aug"].shape == (GpuTrainAugment.N_FLOATS,) and np.array_equal(a["aug"], b["aug"])
+    post = TrainPostDataset(str(tile_dir / "train"), "post", False)
+    assert post[0]["tiles_post"].shape == (1024, 1024, 3)
+    import random
+    draws = np.stack([GpuTrainAugment().draw(random.Random(s), 1024, 1024, 2) for s in range(4000)])
+    zoom = draws[:, 15] == 1
+    assert 0.17 < zoom.mean() < 0.23 and np.all(draws[zoom, 2] <= 1331) and np.all(draws[zoom, 2] >= 1024)
+    assert np.allclose(draws[~zoom, :4], [1, 1, 1024, 1024])
+    assert 0.30 < draws[:, 6].mean() < 0.36 and 0.30 < draws[:, 7].mean() < 0.36
+    assert 0.08 < (draws[:, 8] > 0).mean() < 0.12 and 0.08 < (draws[:, 9] > 0).mean() < 0.12
+    on = draws[:, 8] > 0
+    assert np.all(draws[on, 8] ** 2 >= 10 - 1e-3) and np.all(draws[on, 8] ** 2 <= 50 + 1e-3)
+    bc = (draws[:, 10] != 1) | (draws[:, 11] != 0)
+    assert 0.17 < bc.mean() < 0.23 and np.all(np.abs(draws[:, 10] - 1) <= 0.2 + 1e-6) and np.all(np.abs(draws[:, 11]) <= 0.2 + 1e-6)
+    # per-image independence (intensity_aug is called once per image, pytorch_loader.py:45-51)
+    assert ((draws[:, 8] > 0) != (draws[:, 9] > 0)).mean() > 0.1
+
+
+def test_augmentation_restatement_matches_cv2_resampling():
+    """The float32 per-output-pixel restatement the device kernel is tested against reproduces cv2.resize (INTER_CUBIC for the
+    image within one grey level on a vanishing fraction of pixels, INTER_NEAREST for the mask exactly)."""
+    import cv2
+
+    rng = np.random.default_rng(0)
+    img = cv2.resize(rng.integers(0, 256, (64, 64, 3)).astype(np.uint8), (256, 256), interpolation=cv2.INTER_LINEAR)
+    mask = (rng.random((256, 256)) > 0.97).astype(np.uint8)
+    for scale in (1.07, 1.17, 1.3):
+        ws, hs = int(256 * scale), int(256 * scale)
+        P = np.zeros(16, np.float32)
+        P[0], P[1], P[2], P[3], P[10], P[12], P[15] = 256 / ws, 256 / hs, ws, hs, 1, 1, 1
+        ref = cv2.resize(img, (ws, hs), interpolation=cv2.INTER_CUBIC)
+        refm = cv2.resize(mask, (ws, hs), interpolation=cv2.INTER_NEAREST)
+        u8, _, m = OF.augment_restatement(img, None, mask, P, (10, 20), crop=128)
+        d = np.abs(u8.astype(int) - ref[20:148, 10:138].astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3
+        assert np.array_equal(m, refm[20:148, 10:138])
+    # crop origin: the chosen crop always contains the selected non-zero pixel
+    P[15] = 0
+    P[:4] = [1, 1, 256, 256]
+    yy, xx = np.nonzero(mask)
+    for u in ((0.0, 0.0, 0.0), (0.5, 0.3, 0.9), (0.999, 0.999, 0.999)):
+        px, py = OF.crop_origin_restatement(mask, P, u, crop=128)
+        k = min(int(np.floor(np.float32(u[0]) * np.float32(len(yy)))), len(yy) - 1)
+        assert 0 <= px <= 128 and 0 <= py <= 128 and px <= xx[k] < px + 128 and py <= yy[k] < py + 128
 
 
 def test_normalize_constants_match_albumentations():

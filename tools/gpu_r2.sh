@@ -29,6 +29,8 @@ for s in $STAGES; do
     scale2|scale4|scale8) n=${s#scale}; for c in ${CFGS:-c2}; do
         timeout -k 10 ${SCALE_TIMEOUT:-240} $TR --nproc-per-node $n --master-port 295$n bench.py --config $c --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_${c}_n$n${TAG:-}.json 2> gpurun_out/scale_${c}_n$n${TAG:-}.err
         python tools/show_bench.py gpurun_out/scale_${c}_n$n${TAG:-}.json | head -3; tail -3 gpurun_out/scale_${c}_n$n${TAG:-}.err | cut -c1-300; done ;;
+    loader) timeout 600 python tools/loader_bench.py --tiles 48 > gpurun_out/loader_bench.txt 2> gpurun_out/loader_bench.err; tail -2 gpurun_out/loader_bench.txt; tail -3 gpurun_out/loader_bench.err ;;
+    tests_new) timeout 900 python -m pytest tests/test_augment_gpu.py tests/test_postprocess_gpu.py -q --no-header -p no:cacheprovider --tb=short > gpurun_out/tests_new.log 2>&1; tail -30 gpurun_out/tests_new.log | cut -c1-300 ;;
     *) echo "unknown stage $s" ;;
   esac
 done

@@ -10,9 +10,12 @@ What differs from the reference (by design):
     compute of batch i.  Batches are dicts of DEVICE tensors {"tiles", ["tiles_post"], "mask"} that ``Model._image`` accepts;
   * tiles are sharded over data-parallel ranks with DistributedSampler semantics (index i -> rank i mod N, padded by wrap-around).
 
-The train-time augmentations are restated from albumentations 0.5.1 (not installed here) on uint8 host arrays:
-RandomScale(p=.2, 1.0-1.3x, cubic) -> CropNonEmptyMaskIfExists(512) -> H/V flip (p=.33) -> GaussNoise(p=.1) ->
-RandomBrightnessContrast(p=.2).  ``--autoaugment`` (PIL ImageNet policy) is outside the accelerated path.
+The train-time augmentations (albumentations 0.5.1, not installed here: RandomScale(p=.2, 1.0-1.3x, cubic) ->
+CropNonEmptyMaskIfExists(512) -> H/V flip (p=.33) -> GaussNoise(p=.1) -> RandomBrightnessContrast(p=.2) -> Normalize) run ON THE
+DEVICE by default: the training datasets hand over the full decoded tile plus a dozen host-drawn decisions per sample
+(``GpuTrainAugment``), and one gather kernel per batch (xv2_augment_tiles; crop origin from the mask content by xv2_crop_origin)
+writes the normalised 512^2 crops.  ``XV2_HOST_AUG=1`` selects the host restatement (``TrainAugment``, uint8 numpy / cv2)
+instead.  ``--autoaugment`` (PIL ImageNet policy) is outside the accelerated path.
 """
 import os
 import random
@@ -134,6 +137,41 @@ class TrainAugment:
         return np.ascontiguousarray(img), np.ascontiguousarray(lbl)
 
 
+class GpuTrainAugment:
+    """Host half of the device-side augmentation: draws the per-sample DECISIONS (19 floats: the 16-float parameter block of
+    xv2_augment_tiles + 3 uniforms for the crop origin); every pixel is touched on the GPU only."""
+
+    N_FLOATS = 19
+
+    def __init__(self, crop=512):
+        self.crop = crop
+
+    def draw(self, rng, h, w, n_images):
+        p = np.zeros(self.N_FLOATS, np.float32)
+        ws, hs = w, h
+        if rng.random() < 0.2:  # A.RandomScale(p=0.2, scale_limit=(0, 0.3)): cv2.resize to int(size * scale)
+            scale = rng.uniform(1.0, 1.3)
+            ws, hs = int(w * scale), int(h * scale)
+            p[15] = 1.0
+        p[0], p[1], p[2], p[3] = w / ws, h / hs, ws, hs
+        p[6] = float(rng.random() < 0.33)   # A.HorizontalFlip(p=0.33)
+        p[7] = float(rng.random() < 0.33)   # A.VerticalFlip(p=0.33)
+        for im in range(2):
+            on = im < n_images
+            p[8 + im] = rng.uniform(10.0, 50.0) ** 0.5 if (on and rng.random() < 0.1) else 0.0   # A.GaussNoise(p=0.1), per image
+            if on and rng.random() < 0.2:                                                        # A.RandomBrightnessContrast(p=0.2)
+                p[10 + 2 * im], p[11 + 2 * im] = 1.0 + rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2)
+            else:
+                p[10 + 2 * im], p[11 + 2 * im] = 1.0, 0.0
+        p[14] = float(rng.randrange(1 << 24))
+        p[16:19] = [rng.random(), rng.random(), rng.random()]
+        return p
+
+
+def gpu_augment_enabled():
+    return os.environ.get("XV2_HOST_AUG", "0") != "1"
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # datasets: __getitem__ -> {"tiles": u8 HxWx3 (BGR), ["tiles_post": u8 HxWx3], "mask": u8 HxW}
 # ---------------------------------------------------------------------------------------------------------------
@@ -158,9 +196,15 @@ class TrainPreDataset(_Dataset):
         frame = _read_index(path)
         self.idx = frame["idx"].tolist() if frame is not None else list(range(len(self.imgs_pre)))
         self.aug = TrainAugment(512)
+        self.gpu_aug = GpuTrainAugment(512) if gpu_augment_enabled() else None
+        if self.gpu_aug is not None:
+            self.out_size = 1024  # the ring carries the full decoded tile; the 512^2 crop is cut on the device
 
     def __getitem__(self, idx):
         img, lbl = load_pair(self.imgs_pre[self.idx[idx]], self.lbls_pre[self.idx[idx]])
+        if self.gpu_aug is not None:
+            rng, _ = self._rngs(idx)
+            return {"tiles": img, "mask": lbl, "aug": self.gpu_aug.draw(rng, lbl.shape[0], lbl.shape[1], 1)}
         img, lbl = self.aug(*self._rngs(idx), img, lbl)
         return {"tiles": img, "mask": lbl}
 
@@ -184,10 +228,17 @@ class TrainPostDataset(_Dataset):
         else:
             self.idx = list(range(len(self.imgs_pre)))
         self.aug = TrainAugment(512)
+        self.gpu_aug = GpuTrainAugment(512) if gpu_augment_enabled() else None
+        if self.gpu_aug is not None:
+            self.out_size = 1024
 
     def __getitem__(self, idx):
         img_pre, _ = load_pair(self.imgs_pre[self.idx[idx]], self.lbls_pre[self.idx[idx]])
         img_post, lbl = load_pair(self.imgs_post[self.idx[idx]], self.lbls_post[self.idx[idx]])
+        if self.gpu_aug is not None:
+            rng, _ = self._rngs(idx)
+            return {"tiles": img_pre, "tiles_post": img_post, "mask": lbl,
+                    "aug": self.gpu_aug.draw(rng, lbl.shape[0], lbl.shape[1], 2)}
         img, lbl = self.aug(*self._rngs(idx), np.concatenate((img_pre, img_post), axis=2), lbl)
         return {"tiles": np.ascontiguousarray(img[:, :, :3]), "tiles_post": np.ascontiguousarray(img[:, :, 3:]), "mask": lbl}
 
@@ -267,8 +318,10 @@ class TileLoader:
             return
         size = self.dataset.out_size
         post = getattr(self.dataset, "mode", "pre") == "post" or isinstance(self.dataset, TrainPostDataset)
+        gpu_aug = getattr(self.dataset, "gpu_aug", None)
         if self._ring is None or self._ring.batch != self.batch_size or self._ring.hw != (size, size):
-            self._ring = TileRing(self.batch_size, size, size, post=post, slots=self.slots, device=self.device)
+            extra = {"aug": ((GpuTrainAugment.N_FLOATS,), torch.float32)} if gpu_aug is not None else None
+            self._ring = TileRing(self.batch_size, size, size, post=post, slots=self.slots, device=self.device, extra=extra)
             self._ring.batch, self._ring.hw = self.batch_size, (size, size)
         ring = self._ring
         with ThreadPoolExecutor(self.num_workers) as pool:
@@ -291,6 +344,15 @@ class TileLoader:
                     pending[nxt] = decode(nxt)
                 dev = ring.acquire(i)
                 n = len(batches[i])
+                if gpu_aug is not None:
+                    # the whole augmentation chain + Normalize as one gather kernel on the uploaded uint8 tiles
+                    from .. import ops
+                    aug = dev["aug"][:n]
+                    image, mask, _ = ops.augment_tiles(dev["tiles"][:n], dev["tiles_post"][:n] if "tiles_post" in dev else None,
+                                                       dev["mask"][:n], aug[:, :16], aug[:, 16:19], crop=gpu_aug.crop)
+                    ring.release(i)  # the crops are new tensors: the slot may be refilled as soon as the kernel has run
+                    yield {"image": image, "mask": mask}
+                    continue
                 yield {k: v[:n] for k, v in dev.items()}
                 ring.release(i)
 

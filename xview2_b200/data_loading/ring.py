@@ -17,14 +17,21 @@ import torch
 
 
 class TileRing:
-    def __init__(self, batch, h, w, post=False, slots=2, device=None):
+    def __init__(self, batch, h, w, post=False, slots=2, device=None, extra=None):
+        """`extra`: {name: (shape per sample, dtype)} of additional per-sample host arrays that travel with the tiles (e.g. the
+        augmentation decisions of the device-side train augmentation)."""
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.slots = slots
         self.post = post
         names = ["tiles", "mask"] + (["tiles_post"] if post else [])
         shape = {"tiles": (batch, h, w, 3), "tiles_post": (batch, h, w, 3), "mask": (batch, h, w)}
-        self._host = [{k: torch.empty(shape[k], dtype=torch.uint8).pin_memory() for k in names} for _ in range(slots)]
-        self._dev = [{k: torch.empty(shape[k], dtype=torch.uint8, device=self.device) for k in names} for _ in range(slots)]
+        dtypes = {k: torch.uint8 for k in names}
+        for k, (shp, dt) in (extra or {}).items():
+            names.append(k)
+            shape[k] = (batch, *shp)
+            dtypes[k] = dt
+        self._host = [{k: torch.empty(shape[k], dtype=dtypes[k]).pin_memory() for k in names} for _ in range(slots)]
+        self._dev = [{k: torch.empty(shape[k], dtype=dtypes[k], device=self.device) for k in names} for _ in range(slots)]
         self.stream = torch.cuda.Stream(device=self.device)
         self._ready = [torch.cuda.Event() for _ in range(slots)]
         self._free = [torch.cuda.Event() for _ in range(slots)]
@@ -32,7 +39,7 @@ class TileRing:
             e.record(torch.cuda.current_stream(self.device))
         self._submitted = [False] * slots
         self.batch, self.hw = batch, (h, w)
-        self.bytes_per_batch = sum(t.numel() for t in self._host[0].values())
+        self.bytes_per_batch = sum(t.numel() * t.element_size() for t in self._host[0].values())
 
     def host(self, i):
         """Pinned host tensors of slot i (fill them in place; `.numpy()` views share the memory)."""

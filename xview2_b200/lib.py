@@ -78,6 +78,9 @@ _SIGNATURES = {
     "xv2_post_process": [P, P, I64, P, P, P],
     "xv2_post_process_probs": [P, P, I64, P, P, P],
     "xv2_save_probs": [P, I32, I64, I32, P, P],
+    "xv2_cc_majority_vote": [P, P, P, P, I32, I32, I32, P],
+    "xv2_dilate_square": [P, P, I32, I32, I32, I32, P],
+    "xv2_score_counts": [P, P, P, P, I64, P, P],
     "xv2_splat_bn_gap": [P, P, P, P, I32, I64, I32, P],
     "xv2_splat_bn_combine": [P, P, P, P, P, I32, I64, I32, P],
     "xv2_splat_bn_bwd_partials": [P, P, P, P, P, I32, I64, I32, P],
@@ -98,6 +101,8 @@ _SIGNATURES = {
     "xv2_head_fwd": [P, P, P, P, I64, I32, I32, I32, P],
     "xv2_head_bwd": [P, P, P, P, P, P, I64, I32, I32, I32, P],
     "xv2_normalize_tiles": [P, P, P, I32, I32, I32, I32, P],
+    "xv2_crop_origin": [P, P, P, P, P, I32, I32, I32, I32, I32, I32, P],
+    "xv2_augment_tiles": [P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, P],
     "xv2_adamw": [P, P, P, P, I64, F, F, F, F, F, I32, F, P],
     "xv2_sgd": [P, P, P, I64, F, F, F, I32, P],
     "xv2_adamw_dev": [P, P, P, P, I64, P, P],

@@ -1284,6 +1284,41 @@ def post_process_probs(loc, dmg):
     return pre, post
 
 
+def cc_majority_vote(post_map):
+    """utils/post_process.py:39-43 on the device: (n, h, w) | (h, w) uint8 damage map -> same shape, every 4-connected building
+    carrying its majority class."""
+    single = post_map.dim() == 2
+    m = (post_map[None] if single else post_map).contiguous()
+    n, h, w = m.shape
+    lib.init(m.device.index)
+    out = torch.empty_like(m)
+    labels = torch.empty(n * h * w, dtype=torch.int32, device=m.device)
+    votes = torch.empty((n * h * w, 4), dtype=torch.int32, device=m.device)
+    call("xv2_cc_majority_vote", ptr(m), ptr(out), ptr(labels), ptr(votes), n, h, w)
+    return out[0] if single else out
+
+
+def dilate_square(label_map, k):
+    """post_process.py:44-45 (skimage dilation(img, square(k))) on the device, k odd."""
+    single = label_map.dim() == 2
+    m = (label_map[None] if single else label_map).contiguous()
+    n, h, w = m.shape
+    lib.init(m.device.index)
+    out = torch.empty_like(m)
+    call("xv2_dilate_square", ptr(m), ptr(out), n, h, w, int(k))
+    return out[0] if single else out
+
+
+def score_counts(loc_pred, dmg_pred, loc_targ, dmg_targ, counters=None):
+    """utils/xview2_metrics.py:61-92: accumulates the 15 TP / FN / FP counters of the xView2 scorer over uint8 label maps."""
+    lib.init(loc_pred.device.index)
+    if counters is None:
+        counters = torch.zeros(15, dtype=torch.int64, device=loc_pred.device)
+    call("xv2_score_counts", ptr(loc_pred.contiguous()), ptr(dmg_pred.contiguous()), ptr(loc_targ.contiguous()),
+         ptr(dmg_targ.contiguous()), loc_pred.numel(), ptr(counters))
+    return counters
+
+
 def save_probs(logits):
     """Model.save (plt.py:126-131): (n, h, w) sigmoid(logit[:, 1]) for the 2-class head, (n, 4, h, w) softmax (plain
     NCHW, the layout np.save receives) for the 4-class head."""
@@ -1303,6 +1338,35 @@ def normalize_tiles(pre_u8, post_u8=None, dtype=torch.bfloat16):
     call("xv2_normalize_tiles", ptr(pre_u8.contiguous()), ptr(None if post_u8 is None else post_u8.contiguous()),
          ptr(out), n, h, w, dtype_code(out))
     return out
+
+
+AUG_PARAMS = 16  # floats per sample, layout in include/xv2.h (xv2_augment_tiles)
+
+
+def augment_tiles(pre_u8, post_u8, mask_u8, params, uniforms=None, crop=512, dtype=torch.bfloat16, want_u8=False):
+    """Device-side train augmentation (pytorch_loader.py:73-92,124-148): uint8 (n, H, W, 3) decoded tiles [+ post] and the
+    (n, H, W) mask -> normalised (n, 3|6, crop, crop) channels-last activations + the (n, crop, crop) mask crop.
+    `params`: (n, 16) fp32 host-drawn decisions (see include/xv2.h); `uniforms` (n, 3): when given, the crop origin is chosen
+    ON THE DEVICE from the mask content (CropNonEmptyMaskIfExists), else params[:, 4:6] is used."""
+    n, sh, sw, _ = pre_u8.shape
+    dev = pre_u8.device
+    lib.init(dev.index)
+    params = params.to(device=dev, dtype=torch.float32).contiguous()
+    origin = None
+    if uniforms is not None:
+        max_rows = int(sh * 1.3) + 2
+        rowcount = torch.empty((n, max_rows), dtype=torch.int32, device=dev)
+        origin = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        call("xv2_crop_origin", ptr(mask_u8.contiguous()), ptr(params), ptr(uniforms.to(device=dev, dtype=torch.float32).contiguous()),
+             ptr(rowcount), ptr(origin), n, sh, sw, max_rows, crop, crop)
+    ch = 3 if post_u8 is None else 6
+    out = empty_act(n, ch, crop, crop, dtype, dev)
+    out_u8 = torch.empty((n, crop, crop, ch), dtype=torch.uint8, device=dev) if want_u8 else None
+    mask_out = torch.empty((n, crop, crop), dtype=torch.uint8, device=dev)
+    call("xv2_augment_tiles", ptr(pre_u8.contiguous()), ptr(None if post_u8 is None else post_u8.contiguous()),
+         ptr(mask_u8.contiguous()), ptr(params), ptr(origin), ptr(out), ptr(out_u8), ptr(mask_out), n, sh, sw, crop, crop,
+         dtype_code(out))
+    return (out, mask_out, origin, out_u8) if want_u8 else (out, mask_out, origin)
 
 
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):

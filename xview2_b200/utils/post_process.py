@@ -7,12 +7,12 @@ reads ``<results>/probs/*localization*.npy`` (h, w) and ``*damage*.npy`` (4, h, 
 
   * the per-pixel rule (``post = argmax(dmg) + 1``; ``pre = loc > 0.3 | (loc > 0.1 & post > 1)``; ``post *= pre``, lines :31-38)
     runs on the GPU (xv2_post_process_probs), batched over files with the .npy reads / PNG writes on a thread pool;
-  * ``--components`` (:39-43): every connected building (scipy.ndimage.label, 4-connectivity like the reference) takes its
-    majority damage class -- one bincount over (component, class) pairs instead of a Python loop per building; ties go to the
-    smallest class like ``np.unique`` + ``argmax``;
-  * ``--dilate`` (:44-45): grey-scale dilation with a square footprint (= skimage ``dilation(img, square(k))``, which is not
-    installed here; scipy.ndimage.grey_dilation is the same operator).
-The two optional steps stay on the host exactly as in the reference (SURVEY.md 8f-3 lists their GPU versions as "next").
+  * ``--components`` (:39-43): every connected building (4-connectivity, scipy.ndimage.label's default like the reference) takes
+    its majority damage class; on the device by union-find label equivalence + one (component, class) histogram
+    (xv2_cc_majority_vote); ties go to the smallest class like ``np.unique`` + ``argmax``;
+  * ``--dilate`` (:44-45): grey-scale dilation with a square footprint (skimage ``dilation(img, square(k))``) on the device
+    (xv2_dilate_square, odd k; even k falls back to scipy.ndimage.grey_dilation, the same operator).
+``majority_vote`` / ``dilate`` below are the host formulations (numpy / scipy) the device kernels are tested against.
 """
 import os
 from argparse import ArgumentDefaultsHelpFormatter, ArgumentParser
@@ -70,10 +70,18 @@ def post_process(args, pre_path, post_path, out_dir):
         post = dmg.astype(np.uint8)
         pre = ((loc > 0.3) | ((loc > 0.1) & (post > 1))).astype(np.uint8)
         post = post * pre
-    if args.components:
-        post = majority_vote(post)
-    if args.dilate:
-        pre, post = dilate(pre, args.dilation_rate), dilate(post, args.dilation_rate)
+    if args.components or args.dilate:
+        import torch
+
+        from .. import ops
+        pre_d, post_d = torch.from_numpy(np.ascontiguousarray(pre, np.uint8)).cuda(), torch.from_numpy(np.ascontiguousarray(post, np.uint8)).cuda()
+        if args.components:
+            post_d = ops.cc_majority_vote(post_d)
+        if args.dilate and args.dilation_rate % 2 == 1:
+            pre_d, post_d = ops.dilate_square(pre_d, args.dilation_rate), ops.dilate_square(post_d, args.dilation_rate)
+        pre, post = pre_d.cpu().numpy(), post_d.cpu().numpy()
+        if args.dilate and args.dilation_rate % 2 == 0:
+            pre, post = dilate(pre, args.dilation_rate), dilate(post, args.dilation_rate)
     for arr, path in ((pre, pre_path), (post, post_path)):
         Image.fromarray(arr.astype(np.uint8)).save(os.path.join(out_dir, os.path.basename(path).replace(".npy", "_prediction.png")))
 
