@@ -130,6 +130,76 @@ __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const __nv_bfloat1
   }
 }
 
+// Faster variant for even output widths: lane = OUTPUT CHANNEL (27 accumulators per lane), a block stages the three input rows
+// of one output row in shared memory as fp32 (front-padded by 3 floats so that the patch of an even output pixel starts on a
+// 16-byte boundary) and every warp walks pixel PAIRS: 12 broadcast LDS.128 + 2 coalesced dy loads feed 54 FFMAs per lane, so the
+// FMA pipe, not the shared-memory port, bounds the loop (the (tap, c)-per-lane kernel above re-stages 64-pixel tiles and spends
+// most of its time there: 7 TFLOP/s).
+template <int K>
+__global__ void __launch_bounds__(256) stem_conv_wgrad_rows_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                   const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw,
+                                                                   int n, int h, int wd, int oh, int ow) {
+  extern __shared__ __align__(16) float xs_dyn[];
+  const int row_len = ((3 + 3 * wd + 16) + 3) & ~3;  // floats per staged input row
+  float* xs = xs_dyn;                                 // [3][row_len]
+  __shared__ float red[27][K];
+  for (int i = threadIdx.x; i < 27 * K; i += blockDim.x) red[i / K][i % K] = 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int KH = K / 32;
+  float acc[KH][27];
+#pragma unroll
+  for (int a = 0; a < KH; ++a)
+#pragma unroll
+    for (int j = 0; j < 27; ++j) acc[a][j] = 0.f;
+  const long long rows = (long long)n * oh;
+  const int pairs = ow / 2;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int oy = (int)(row % oh), img = (int)(row / oh);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * row_len; i += blockDim.x) {
+      const int rr = i / row_len, j = i - rr * row_len;
+      const int iy = 2 * oy - 1 + rr;
+      const int e = j - 3;  // element index within the (wd * 3)-long input row; < 0 is the left zero padding
+      float v = 0.f;
+      if (iy >= 0 && iy < h && e >= 0 && e < 3 * wd) v = __bfloat162float(x[((long long)img * h + iy) * wd * 3 + e]);
+      xs[i] = v;
+    }
+    __syncthreads();
+    const __nv_bfloat16* dyr = dy + row * ow * K;
+    for (int pp = warp; pp < pairs; pp += 8) {
+      float f[3][16];
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        const float4* src = reinterpret_cast<const float4*>(xs + rr * row_len + 12 * pp);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = src[q];
+          f[rr][4 * q] = t.x; f[rr][4 * q + 1] = t.y; f[rr][4 * q + 2] = t.z; f[rr][4 * q + 3] = t.w;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < KH; ++a) {
+        const float d0 = __bfloat162float(dyr[(long long)(2 * pp) * K + a * 32 + lane]);
+        const float d1 = __bfloat162float(dyr[(long long)(2 * pp + 1) * K + a * 32 + lane]);
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int j = 0; j < 9; ++j) acc[a][rr * 9 + j] = fmaf(d0, f[rr][j], fmaf(d1, f[rr][6 + j], acc[a][rr * 9 + j]));
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < KH; ++a)
+#pragma unroll
+    for (int j = 0; j < 27; ++j) atomicAdd(&red[j][a * 32 + lane], acc[a][j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * K; i += blockDim.x) {
+    const int k = i / 27, tpi = i % 27;
+    atomicAdd(dw + i, red[tpi][k]);
+  }
+}
+
 // ---- fully connected on [n][c] vectors (n <= 32): y[n][k] = b[k] + sum_c x[n][c] w[k][c]; one warp per output channel ------------
 constexpr int kFcRows = 8;
 __global__ void __launch_bounds__(256) fc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -214,6 +284,27 @@ extern "C" int xv2_stem_conv_wgrad(const void* x, const void* dy, float* dw, int
     return XV2_EUNSUPPORTED;
   }
   const int oh = (h - 1) / 2 + 1, ow = (wd - 1) / 2 + 1;
+  if (ow % 2 == 0 && wd % 2 == 0 && wd <= 4096) {
+    const size_t smem = 3 * (size_t)(((3 + 3 * wd + 16) + 3) & ~3) * sizeof(float);
+    long long blocks2 = (long long)n * oh;
+    if (blocks2 > 4LL * kNumSMs) blocks2 = 4LL * kNumSMs;
+    cudaError_t e = cudaSuccess;
+    if (k == 32) {
+      if (smem > 48 * 1024) e = cudaFuncSetAttribute(stem_conv_wgrad_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess)
+        stem_conv_wgrad_rows_kernel<32><<<(unsigned)blocks2, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, n, h, wd, oh, ow);
+    } else {
+      if (smem > 48 * 1024) e = cudaFuncSetAttribute(stem_conv_wgrad_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess)
+        stem_conv_wgrad_rows_kernel<64><<<(unsigned)blocks2, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, n, h, wd, oh, ow);
+    }
+    if (e != cudaSuccess) {
+      set_error("stem_conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return XV2_ECUDA;
+    }
+    XV2_LAUNCH_CHECK();
+    return XV2_OK;
+  }
   const int blocks = 6 * kNumSMs;
   if (k == 32)
     stem_conv_wgrad_kernel<32><<<blocks, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, n, h,
