@@ -77,6 +77,9 @@ struct alignas(64) TcParams {
   CUtensorMap map_out;
   int tma_store;           // 0: direct register -> global stores
   int store_c;             // channels per staged block (64 -> 128B swizzle, 32 -> 64B swizzle)
+  int out_bufs;            // staging buffers per epilogue half: 2 for single-tap (1x1 / transposed) convolutions, whose main loop
+                           // is one or two k-blocks long -- there the epilogue is the critical path and a second buffer lets the
+                           // next block be converted while the TMA store of the previous one is still reading shared memory
   double* stats;           // optional fp64 [2 * k_total]: BN sum / sum of squares of the rounded outputs
   // optional inference epilogue: y = act(ep_scale[k] * conv + ep_shift[k])  (eval-mode BatchNorm + activation folded in)
   const float* ep_scale;
@@ -97,8 +100,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   const uint32_t bar_base = base + p.stages * stage_bytes;
   const uint32_t full0 = bar_base, empty0 = bar_base + 64, tfull0 = bar_base + 128, tempty0 = bar_base + 144;
   const uint32_t tmem_slot = bar_base + 160;
-  const uint32_t stage_out0 = (bar_base + 256 + 1023u) & ~1023u;  // 2 x 16 KB output staging (one per epilogue half)
-  const uint32_t stats_sm = stage_out0 + 2 * 16384;                // float [2 * k_total] when p.stats
+  const uint32_t stage_out0 = (bar_base + 256 + 1023u) & ~1023u;  // 2 x out_bufs x 16 KB output staging (per epilogue half)
+  const uint32_t stats_sm = stage_out0 + 2 * p.out_bufs * 16384;   // float [2 * k_total] when p.stats
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int epi_warps = p.tma_store ? 8 : 4;
 
@@ -217,12 +220,11 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     const int half = (warp - 2) >> 2;
     const int m = q * 32 + lane;       // row of the tile (pixel)
     const bool issuer = (q == ((2 + 4 * half) & 3)) && lane == 0;  // lane 0 of the half's first warp
-    const uint32_t sbuf = stage_out0 + half * 16384;
+    const uint32_t sbuf0 = stage_out0 + half * p.out_bufs * 16384;
     const int nblocks = p.bn / p.store_c;
     const uint32_t rowb = (uint32_t)p.store_c * 2;
-    const uint32_t row_addr = sbuf + m * rowb;
     const uint32_t swz = p.store_c == 64 ? (uint32_t)(m & 7) : (uint32_t)((m >> 1) & 3);
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, obuf = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       int t = tile / p.n_tiles;
@@ -244,7 +246,12 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
       for (int sb = half; sb < nblocks; sb += 2) {
-        if (issuer) bulk_wait_read0();  // the previous TMA store out of this half's buffer has been read
+        const uint32_t sbuf = sbuf0 + obuf * 16384;
+        const uint32_t row_addr = sbuf + m * rowb;
+        if (issuer) {  // the TMA store that last read THIS buffer has finished reading it
+          if (p.out_bufs == 2) bulk_wait_read1();
+          else bulk_wait_read0();
+        }
         named_bar_sync(1 + half, 128);
         for (int part = 0; part < p.store_c; part += 32) {
           const int col = sb * p.store_c + part;
@@ -342,6 +349,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
             asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa + 4 * p.k_total), "f"(v2 + q0), "f"(v3 + q1) : "memory");
           }
         }
+        if (p.out_bufs == 2) obuf ^= 1;
       }
       tc_fence_before();
       __syncwarp();
@@ -803,6 +811,7 @@ static int conv_tc_impl(const xv2_tc_conv* q, const void* src0, const void* src1
 
   TcParams p;
   memset(&p, 0, sizeof(p));
+  p.out_bufs = 1;
   if (gather) {
     rc = encode_gather2x2_map(&p.map_a0, src0, q->n, q->h, q->w, q->c0, ld0, bk, tw, th);
   } else {
@@ -843,7 +852,8 @@ static int conv_tc_impl(const xv2_tc_conv* q, const void* src0, const void* src1
     rc = convt ? encode_out_shuffle_map(&p.map_out, out, q->n, q->h, q->w, q->k, p.store_c, tw, th)
                : encode_out_map(&p.map_out, out, (long long)q->n * q->h * q->w, q->k, ldo, p.store_c);
     if (rc) return rc;
-    extra = 1024 + 2 * 16384 + (stats ? 8u * q->k : 0u);
+    p.out_bufs = (taps == 1) ? 2 : 1;
+    extra = 1024 + 2 * p.out_bufs * 16384 + (stats ? 8u * q->k : 0u);
     p.stats = stats;
     p.ep_scale = ep_scale;
     p.ep_shift = ep_shift;

@@ -1244,7 +1244,8 @@ def ordinal_labels(logits, loss_str, labels=None, counters=None, clamp4=True, wa
     n, _, h, w = logits.shape
     u8 = torch.empty((n, h, w), dtype=torch.uint8, device=logits.device) if want_u8 else None
     f32 = torch.empty((n, h, w), dtype=torch.float32, device=logits.device) if want_f32 else None
-    call("xv2_ordinal_labels", ptr(logits), ptr(labels.contiguous()) if labels is not None else None, n * h * w,
+    labels_c = labels.contiguous() if labels is not None else None
+    call("xv2_ordinal_labels", ptr(logits), ptr(labels_c), n * h * w,
          ORDINAL_MODE[loss_str], int(clamp4), ptr(counters), ptr(u8), ptr(f32))
     return u8 if want_u8 else f32
 
@@ -1314,8 +1315,8 @@ def score_counts(loc_pred, dmg_pred, loc_targ, dmg_targ, counters=None):
     lib.init(loc_pred.device.index)
     if counters is None:
         counters = torch.zeros(15, dtype=torch.int64, device=loc_pred.device)
-    call("xv2_score_counts", ptr(loc_pred.contiguous()), ptr(dmg_pred.contiguous()), ptr(loc_targ.contiguous()),
-         ptr(dmg_targ.contiguous()), loc_pred.numel(), ptr(counters))
+    lp, dp, lt, dt = (t.contiguous() for t in (loc_pred, dmg_pred, loc_targ, dmg_targ))  # named: copies outlive the launch call
+    call("xv2_score_counts", ptr(lp), ptr(dp), ptr(lt), ptr(dt), lp.numel(), ptr(counters))
     return counters
 
 
@@ -1335,8 +1336,9 @@ def normalize_tiles(pre_u8, post_u8=None, dtype=torch.bfloat16):
     n, h, w, _ = pre_u8.shape
     lib.init(pre_u8.device.index)
     out = empty_act(n, 3 if post_u8 is None else 6, h, w, dtype, pre_u8.device)
-    call("xv2_normalize_tiles", ptr(pre_u8.contiguous()), ptr(None if post_u8 is None else post_u8.contiguous()),
-         ptr(out), n, h, w, dtype_code(out))
+    pre_c = pre_u8.contiguous()  # named, so that a temporary copy outlives the launch call (see _keep below)
+    post_c = None if post_u8 is None else post_u8.contiguous()
+    call("xv2_normalize_tiles", ptr(pre_c), ptr(post_c), ptr(out), n, h, w, dtype_code(out))
     return out
 
 
@@ -1351,21 +1353,24 @@ def augment_tiles(pre_u8, post_u8, mask_u8, params, uniforms=None, crop=512, dty
     n, sh, sw, _ = pre_u8.shape
     dev = pre_u8.device
     lib.init(dev.index)
+    # every (possibly temporary) contiguous copy gets a NAME: a temporary created inside the call expression would be freed --
+    # and its block handed to the next temporary -- before the kernel is even launched
     params = params.to(device=dev, dtype=torch.float32).contiguous()
+    pre_c, mask_c = pre_u8.contiguous(), mask_u8.contiguous()
+    post_c = None if post_u8 is None else post_u8.contiguous()
     origin = None
     if uniforms is not None:
         max_rows = int(sh * 1.3) + 2
         rowcount = torch.empty((n, max_rows), dtype=torch.int32, device=dev)
         origin = torch.empty((n, 2), dtype=torch.int32, device=dev)
-        call("xv2_crop_origin", ptr(mask_u8.contiguous()), ptr(params), ptr(uniforms.to(device=dev, dtype=torch.float32).contiguous()),
-             ptr(rowcount), ptr(origin), n, sh, sw, max_rows, crop, crop)
+        uni_c = uniforms.to(device=dev, dtype=torch.float32).contiguous()
+        call("xv2_crop_origin", ptr(mask_c), ptr(params), ptr(uni_c), ptr(rowcount), ptr(origin), n, sh, sw, max_rows, crop, crop)
     ch = 3 if post_u8 is None else 6
     out = empty_act(n, ch, crop, crop, dtype, dev)
     out_u8 = torch.empty((n, crop, crop, ch), dtype=torch.uint8, device=dev) if want_u8 else None
     mask_out = torch.empty((n, crop, crop), dtype=torch.uint8, device=dev)
-    call("xv2_augment_tiles", ptr(pre_u8.contiguous()), ptr(None if post_u8 is None else post_u8.contiguous()),
-         ptr(mask_u8.contiguous()), ptr(params), ptr(origin), ptr(out), ptr(out_u8), ptr(mask_out), n, sh, sw, crop, crop,
-         dtype_code(out))
+    call("xv2_augment_tiles", ptr(pre_c), ptr(post_c), ptr(mask_c), ptr(params), ptr(origin), ptr(out), ptr(out_u8),
+         ptr(mask_out), n, sh, sw, crop, crop, dtype_code(out))
     return (out, mask_out, origin, out_u8) if want_u8 else (out, mask_out, origin)
 
 
