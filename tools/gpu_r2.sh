@@ -22,10 +22,11 @@ for s in $STAGES; do
         --log-file gpurun_out/launches.csv python tools/layer_profile.py --ncu > gpurun_out/launches.log 2>&1; wc -l gpurun_out/launches.csv ;;
     traffic) timeout 1500 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
         --profile-from-start off --csv --log-file gpurun_out/traffic.csv python tools/layer_profile.py --ncu > gpurun_out/traffic.log 2>&1; wc -l gpurun_out/traffic.csv ;;
-    ncu_full) # one --set full row per distinct kernel of the step: the first 2 launches of every kernel name
-        timeout 2400 $NCU --set full --clock-control none --import-source on --profile-from-start off --launch-count 2000 \
-        --kernel-id :::1\|2 -f -o gpurun_out/prof_full python tools/layer_profile.py --ncu > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log
-        $NCU -i gpurun_out/prof_full.ncu-rep --page raw --csv > gpurun_out/prof_full_raw.csv 2>/dev/null; wc -l gpurun_out/prof_full_raw.csv ;;
+    ncu_zoo) # one --set full row per kernel family at its C2 shape; the report stays on the box, the CSV comes back
+        timeout 1200 $NCU --set full --clock-control none --profile-from-start off -k regex:"xv2|kernel" -c 150 \
+          -f -o /tmp/prof_zoo python tools/kernel_zoo.py > gpurun_out/ncu_zoo.log 2>&1; tail -3 gpurun_out/ncu_zoo.log
+        $NCU -i /tmp/prof_zoo.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size,smsp__inst_executed.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,lts__t_bytes.sum > gpurun_out/ncu_zoo.csv 2>/dev/null; wc -l gpurun_out/ncu_zoo.csv
+        $NCU -i /tmp/prof_zoo.ncu-rep --page details --csv --section WarpStateStats --section SpeedOfLight > gpurun_out/ncu_zoo_details.csv 2>/dev/null; wc -c gpurun_out/ncu_zoo_details.csv ;;
     scale2|scale4|scale8) n=${s#scale}; for c in ${CFGS:-c2}; do
         timeout -k 10 ${SCALE_TIMEOUT:-240} $TR --nproc-per-node $n --master-port 295$n bench.py --config $c --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_${c}_n$n${TAG:-}.json 2> gpurun_out/scale_${c}_n$n${TAG:-}.err
         python tools/show_bench.py gpurun_out/scale_${c}_n$n${TAG:-}.json | head -3; tail -3 gpurun_out/scale_${c}_n$n${TAG:-}.err | cut -c1-300; done ;;
