@@ -159,6 +159,14 @@ int xv2_bn_train_apply(const void* x, const void* residual, void* y, int64_t pix
 int xv2_bn_bwd_reduce(const void* dy, const void* x, const void* residual, int64_t pixels, int32_t c, int32_t dtype,
                       const float* scale, const float* shift, const float* mean, const float* invstd, int32_t act,
                       double* red, void* stream);
+/* backward pass 1 for an activation whose gradient arrives in two parts (a residual join: the next block's conv1 data gradient
+ * `dy` and its shortcut gradient `dy2`, unet.py:52 Bottleneck.forward `out += residual`): sums them in the kernel instead of an
+ * autograd accumulation pass, writes du = round_bf16(dy [+ dy2]) * act'(u) once (bf16; it is ALSO the shortcut's gradient) and
+ * accumulates red from the rounded du; pass 2 then runs with dy = du, act = none, residual = NULL.  bf16 streaming path only
+ * (XV2_EUNSUPPORTED otherwise: the caller adds the parts and uses xv2_bn_bwd_reduce).  dy2 and residual may be NULL. */
+int xv2_bn_bwd_reduce_du(const void* dy, const void* dy2, const void* x, const void* residual, void* du, int64_t pixels,
+                         int32_t c, int32_t dtype, const float* scale, const float* shift, const float* mean,
+                         const float* invstd, int32_t act, double* red, void* stream);
 /* backward pass 2: dx = gamma*invstd*(du - mean(du) - xhat*mean(du*xhat)) [train] or du*scale [eval: red == NULL];
  * dres (optional) = du; dgamma/dbeta (fp32 [c]) from red: written, or ADDED TO when accumulate != 0 (the parameter's own
  * gradient slot in the flat buffer, so that no separate accumulation launch is needed). */

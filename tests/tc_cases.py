@@ -36,6 +36,7 @@ CASES = {
     "convt_c128_k64": ("convt", 2, 128, 0, 16, 16, 64, 2, 1, 1),
     "convt_c64_k32_w64": ("convt", 1, 64, 0, 8, 64, 32, 2, 1, 1),
     "convt_c2048_k512": ("convt", 1, 2048, 0, 16, 8, 512, 2, 1, 1),
+    "convt_c64_k32_w256": ("convt", 2, 64, 0, 6, 256, 32, 2, 1, 1),    # all four taps in one N tile (dec_l5 shape), row tiles
 }
 
 

@@ -191,11 +191,12 @@ def test_batch_norm_stream(training, act, with_res, c, hw):
         assert rel(bn.running_mean, ref.running_mean) < 1e-3 and rel(bn.running_var, ref.running_var) < 1e-3
 
 
+@pytest.mark.parametrize("hw", [(15, 18), (16, 20)])  # even sizes take the 2x2-quad backward kernels (3x3 / 2 / 1 pools)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_pools(dtype):
+def test_pools(dtype, hw):
     ops = _ops()
     t = tol(dtype)
-    x = rnd(2, 16, 15, 18, dtype=dtype, seed=1).contiguous(memory_format=CL).requires_grad_(True)
+    x = rnd(2, 16, hw[0], hw[1], dtype=dtype, seed=1).contiguous(memory_format=CL).requires_grad_(True)
     # reference in plain NCHW: torch 2.11's CUDA channels-last avg_pool2d BACKWARD is wrong for padded non-square
     # inputs (it disagrees with torch's own CPU and NCHW-CUDA results; tools/dbg_pool.py shows it)
     xr = x.detach().float().contiguous().requires_grad_(True)

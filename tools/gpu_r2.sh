@@ -23,13 +23,17 @@ for s in $STAGES; do
     traffic) timeout 1500 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
         --profile-from-start off --csv --log-file gpurun_out/traffic.csv python tools/layer_profile.py --ncu > gpurun_out/traffic.log 2>&1; wc -l gpurun_out/traffic.csv ;;
     ncu_zoo) # one --set full row per kernel family at its C2 shape; the report stays on the box, the CSV comes back
-        timeout 1200 $NCU --set full --clock-control none --profile-from-start off -k regex:"xv2|kernel" -c 150 \
-          -f -o /tmp/prof_zoo python tools/kernel_zoo.py > gpurun_out/ncu_zoo.log 2>&1; tail -3 gpurun_out/ncu_zoo.log
+        timeout 1200 $NCU --set full --clock-control none --profile-from-start off --kernel-name-base demangled -k regex:"xv2::" -c ${ZOO_COUNT:-120} \
+          -f -o /tmp/prof_zoo python tools/kernel_zoo.py ${ZOO_ARGS:-} > gpurun_out/ncu_zoo.log 2>&1; tail -3 gpurun_out/ncu_zoo.log
         $NCU -i /tmp/prof_zoo.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size,smsp__inst_executed.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,lts__t_bytes.sum > gpurun_out/ncu_zoo.csv 2>/dev/null; wc -l gpurun_out/ncu_zoo.csv
         $NCU -i /tmp/prof_zoo.ncu-rep --page details --csv --section WarpStateStats --section SpeedOfLight > gpurun_out/ncu_zoo_details.csv 2>/dev/null; wc -c gpurun_out/ncu_zoo_details.csv ;;
     scale2|scale4|scale8) n=${s#scale}; for c in ${CFGS:-c2}; do
         timeout -k 10 ${SCALE_TIMEOUT:-240} $TR --nproc-per-node $n --master-port 295$n bench.py --config $c --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_${c}_n$n${TAG:-}.json 2> gpurun_out/scale_${c}_n$n${TAG:-}.err
         python tools/show_bench.py gpurun_out/scale_${c}_n$n${TAG:-}.json | head -3; tail -3 gpurun_out/scale_${c}_n$n${TAG:-}.err | cut -c1-300; done ;;
+    layers_wg) for v in "64 128" "128 128" "64 256"; do set -- $v; XV2_WG_PIX=$1 XV2_WG_BN=$2 timeout 600 python tools/layer_profile.py > gpurun_out/layers_wg_$1_$2.txt 2> gpurun_out/layers.err
+        echo "--- XV2_WG_PIX=$1 XV2_WG_BN=$2"; python tools/layer_sum.py gpurun_out/layers_wg_$1_$2.txt -n 12; tail -2 gpurun_out/layers.err; done ;;
+    dbg_fork) timeout 300 python tools/dbg_fork.py > gpurun_out/dbg_fork.txt 2>&1; tail -12 gpurun_out/dbg_fork.txt ;;
+    tests_sel) timeout 900 python -m pytest tests/test_tc_gpu.py tests/test_blocks_gpu.py tests/test_kernels_gpu.py tests/test_model_gpu.py -q --no-header -p no:cacheprovider --tb=short -k "${TESTS_K:-pools or convt or fork or bottleneck or batch_norm or model}" > gpurun_out/tests_sel.log 2>&1; tail -25 gpurun_out/tests_sel.log | cut -c1-300 ;;
     loader) timeout 600 python tools/loader_bench.py --tiles 48 > gpurun_out/loader_bench.txt 2> gpurun_out/loader_bench.err; tail -2 gpurun_out/loader_bench.txt; tail -3 gpurun_out/loader_bench.err ;;
     tests_new) timeout 900 python -m pytest tests/test_augment_gpu.py tests/test_postprocess_gpu.py -q --no-header -p no:cacheprovider --tb=short > gpurun_out/tests_new.log 2>&1; tail -30 gpurun_out/tests_new.log | cut -c1-300 ;;
     *) echo "unknown stage $s" ;;

@@ -380,8 +380,9 @@ bool bn_stream_ok(int64_t pixels, int c, int dtype);
 int bn_stream_stats(const void* x, int64_t pixels, int c, double* stats, void* stream);
 int bn_stream_apply(const void* x, const void* res, void* y, int64_t pixels, int c, const float* scale, const float* shift,
                     int act, void* stream);
-int bn_stream_bwd_reduce(const void* dy, const void* x, const void* res, int64_t pixels, int c, const float* scale,
-                         const float* shift, const float* mean, const float* invstd, int act, double* red, void* stream);
+int bn_stream_bwd_reduce(const void* dy, const void* dy2, const void* x, const void* res, void* du, int64_t pixels, int c,
+                         const float* scale, const float* shift, const float* mean, const float* invstd, int act, double* red,
+                         void* stream);
 int bn_stream_train_apply(const void* x, const void* res, void* y, int64_t pixels, int c, const double* stats, int64_t count,
                           const float* gamma, const float* beta, float* rmean, float* rvar, float momentum, float eps,
                           float* coef, int act, void* stream);
@@ -463,7 +464,7 @@ extern "C" int xv2_bn_bwd_reduce(const void* dy, const void* x, const void* resi
                                  const float* invstd, int32_t act, double* red, void* stream) {
   XV2_REQUIRE(c > 0 && pixels > 0, "bn_bwd_reduce: empty tensor");
   if (bn_stream_ok(pixels, c, dtype))
-    return bn_stream_bwd_reduce(dy, x, residual, pixels, c, scale, shift, mean, invstd, act, red, stream);
+    return bn_stream_bwd_reduce(dy, nullptr, x, residual, nullptr, pixels, c, scale, shift, mean, invstd, act, red, stream);
   const int vec = pick_vec(c, dtype);
   RowMap m = make_rowmap(c, vec);
   int blocks = pick_blocks(pixels, m, 32);
@@ -474,6 +475,17 @@ extern "C" int xv2_bn_bwd_reduce(const void* dy, const void* x, const void* resi
                                                                         red)));
   XV2_LAUNCH_CHECK();
   return XV2_OK;
+}
+
+extern "C" int xv2_bn_bwd_reduce_du(const void* dy, const void* dy2, const void* x, const void* residual, void* du,
+                                    int64_t pixels, int32_t c, int32_t dtype, const float* scale, const float* shift,
+                                    const float* mean, const float* invstd, int32_t act, double* red, void* stream) {
+  XV2_REQUIRE(c > 0 && pixels > 0 && dy && x && du && red, "bn_bwd_reduce_du: bad argument");
+  if (!bn_stream_ok(pixels, c, dtype)) {
+    set_error("bn_bwd_reduce_du: only the streaming bf16 path (2048 %% c == 0, >= 1 Mi elements) writes du");
+    return XV2_EUNSUPPORTED;
+  }
+  return bn_stream_bwd_reduce(dy, dy2, x, residual, du, pixels, c, scale, shift, mean, invstd, act, red, stream);
 }
 
 extern "C" int xv2_bn_bwd_apply(const void* dy, const void* x, const void* residual, void* dx, void* dres,

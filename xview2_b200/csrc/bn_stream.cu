@@ -24,8 +24,10 @@ enum { BN_STATS = 0, BN_APPLY = 1, BN_BWD_REDUCE = 2, BN_BWD_APPLY = 3 };
 struct BnStreamParams {
   const __nv_bfloat16* in0;   // stats/apply: x;  backward: dy
   const __nv_bfloat16* in1;   // backward: x (the BN input);  apply: residual (or null)
-  const __nv_bfloat16* in2;   // backward: residual (or null)
-  __nv_bfloat16* out0;        // apply: y;  bwd_apply: dx
+  const __nv_bfloat16* in2;   // backward: residual (or the second dy addend when there is no residual)
+  const __nv_bfloat16* in3;   // bwd_reduce: second dy addend when a residual is present
+  int res_slot, dy2_slot;     // backward: staging slot of the residual / of the second dy addend (0 = absent)
+  __nv_bfloat16* out0;        // apply: y;  bwd_apply: dx;  bwd_reduce: du = (dy [+ dy2]) * act'(u), bf16 (or null)
   __nv_bfloat16* out1;        // bwd_apply: dres (or null)
   long long elems;
   int c, act, n_in, stages;
@@ -73,6 +75,7 @@ __device__ __forceinline__ void lds128(uint32_t addr, float* f) {
     f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ void stg128(__nv_bfloat16* p, const float* f) {
   uint32_t w[4];
 #pragma unroll
@@ -142,6 +145,7 @@ __global__ void __launch_bounds__(288, 2) bn_stream_kernel(const BnStreamParams 
         bulk_g2s(dst, p.in0 + e0, bytes, fb);
         if (p.n_in > 1) bulk_g2s(dst + kChunkBytes, p.in1 + e0, bytes, fb);
         if (p.n_in > 2) bulk_g2s(dst + 2 * kChunkBytes, p.in2 + e0, bytes, fb);
+        if (p.n_in > 3) bulk_g2s(dst + 3 * kChunkBytes, p.in3 + e0, bytes, fb);
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(288, 2) bn_stream_kernel(const BnStreamParams 
       k2[i] = (float)(p.red_in[p.c + cbase + i]) * p.inv_n;
     }
   }
-  const bool has_res = (MODE == BN_APPLY) ? (p.n_in > 1) : (p.n_in > 2);
+  const bool has_res = (MODE == BN_APPLY) ? (p.n_in > 1) : (p.res_slot != 0);
   uint32_t s = 0, ph = 0;
   for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     mbar_wait(full0 + 8 * s, ph);
@@ -189,6 +193,12 @@ __global__ void __launch_bounds__(288, 2) bn_stream_kernel(const BnStreamParams 
         lds128(st + v * 16, f0);
         if (p.n_in > 1) lds128(st + kChunkBytes + v * 16, f1);
         if (p.n_in > 2) lds128(st + 2 * kChunkBytes + v * 16, f2);
+        if (MODE == BN_BWD_REDUCE && p.dy2_slot) {  // gradient arriving from two consumers: summed here, not by autograd
+          float f3[8];
+          if (p.dy2_slot == 3) lds128(st + 3 * kChunkBytes + v * 16, f3);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f0[i] = bf16_round(f0[i] + (p.dy2_slot == 3 ? f3[i] : f2[i]));
+        }
         if (MODE == BN_STATS) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -217,6 +227,11 @@ __global__ void __launch_bounds__(288, 2) bn_stream_kernel(const BnStreamParams 
             }
           }
           if (MODE == BN_BWD_REDUCE) {
+            if (p.out0) {  // du is what bwd_apply (act = none) and the residual branch read: sums follow the rounded values
+#pragma unroll
+              for (int i = 0; i < 8; ++i) du[i] = bf16_round(du[i]);
+              stg128(p.out0 + e, du);
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               a1[i] += du[i];
@@ -280,7 +295,7 @@ bool bn_stream_ok(int64_t pixels, int c, int dtype) {
 }
 
 template <int MODE> static int launch_stream(BnStreamParams& p, void* stream) {
-  p.stages = p.n_in == 1 ? 8 : (p.n_in == 2 ? 6 : 4);
+  p.stages = p.n_in == 1 ? 8 : (p.n_in == 2 ? 6 : (p.n_in == 3 ? 4 : 3));
   const size_t smem = (size_t)p.stages * p.n_in * kChunkBytes + 128;
   static bool attr_set = false;
   if (!attr_set) {
@@ -347,17 +362,26 @@ int bn_stream_train_apply(const void* x, const void* res, void* y, int64_t pixel
   p.fin_count = count;
   return launch_stream<BN_APPLY>(p, stream);
 }
-int bn_stream_bwd_reduce(const void* dy, const void* x, const void* res, int64_t pixels, int c, const float* scale,
-                         const float* shift, const float* mean, const float* invstd, int act, double* red, void* stream) {
+int bn_stream_bwd_reduce(const void* dy, const void* dy2, const void* x, const void* res, void* du, int64_t pixels, int c,
+                         const float* scale, const float* shift, const float* mean, const float* invstd, int act, double* red,
+                         void* stream) {
   BnStreamParams p;
   memset(&p, 0, sizeof(p));
   p.in0 = (const __nv_bfloat16*)dy;
   p.in1 = (const __nv_bfloat16*)x;
-  p.in2 = (const __nv_bfloat16*)res;
+  p.n_in = 2;
+  if (res) {
+    p.in2 = (const __nv_bfloat16*)res;
+    p.res_slot = p.n_in++;
+  }
+  if (dy2) {
+    (p.n_in == 2 ? p.in2 : p.in3) = (const __nv_bfloat16*)dy2;
+    p.dy2_slot = p.n_in++;
+  }
+  p.out0 = (__nv_bfloat16*)du;
   p.elems = pixels * c;
   p.c = c;
   p.act = act;
-  p.n_in = res ? 3 : 2;
   p.scale = scale;
   p.shift = shift;
   p.mean = mean;
@@ -373,6 +397,7 @@ int bn_stream_bwd_apply(const void* dy, const void* x, const void* res, void* dx
   p.in0 = (const __nv_bfloat16*)dy;
   p.in1 = (const __nv_bfloat16*)x;
   p.in2 = (const __nv_bfloat16*)res;
+  p.res_slot = res ? 2 : 0;
   p.out0 = (__nv_bfloat16*)dx;
   p.out1 = (__nv_bfloat16*)dres;
   p.elems = pixels * c;

@@ -234,14 +234,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       const int t2 = m_tile / p.tiles_w;
       const int thi = t2 % p.tiles_h;
       const int img = t2 / p.tiles_h;
-      int co0, kh = 0;
-      if (p.convt) {  // N index = (kh, kw, k): a tile lies inside one kh; co0 indexes the contiguous (kw, k) row segment
-        const int nglob = n_tile * p.bn;
-        kh = nglob / (2 * p.k_total);
-        co0 = nglob - kh * 2 * p.k_total;
-      } else {
-        co0 = g * p.kg + n_tile * p.bn;
-      }
+      // transposed conv: N index = (kh, kw, k); a STAGED BLOCK lies inside one kh (the tile may span both): co0 = tile's first N index
+      const int co0 = p.convt ? n_tile * p.bn : g * p.kg + n_tile * p.bn;
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
@@ -284,9 +278,10 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         named_bar_sync(1 + half, 128);
         if (issuer) {
           const int cc = co0 + sb * p.store_c;
-          if (p.convt)
-            tma_store_4d(&p.map_out, sbuf, cc, twi * p.tw, kh, img * p.h + thi * p.th);
-          else
+          if (p.convt) {  // (kw, k) of one kh is a contiguous row segment of the (n, 2h, 2w, k) output
+            const int kh = cc / (2 * p.k_total);
+            tma_store_4d(&p.map_out, sbuf, cc - kh * 2 * p.k_total, twi * p.tw, kh, img * p.h + thi * p.th);
+          } else
             tma_store_2d(&p.map_out, sbuf, cc, ((img * p.h + thi * p.th) * p.w + twi * p.tw));
           bulk_commit();
         }
@@ -456,14 +451,15 @@ struct alignas(64) WgParams {
   int stages;
   int gather2x2;            // tap-shifted operand is the 5-D 2x2 gather view
   int ctot;                 // row length of dW per tap: channels of the shifted operand (all sources, per group)
+  int pix;                  // pixels per pipeline stage (th * tw): 128, or 64 so that two CTAs (3 stages each) share an SM
   float* dw;
 };
 
-__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+__global__ void __launch_bounds__(192, 2) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t ax_bytes = 128u * p.atom_x * 2;  // one M atom box
-  const uint32_t ay_bytes = 128u * p.atom_y * 2;  // one N atom box
-  const uint32_t a_bytes = ax_bytes * p.atoms_per_mtile;  // = 32 KB
+  const uint32_t ax_bytes = (uint32_t)p.pix * p.atom_x * 2;  // one M atom box
+  const uint32_t ay_bytes = (uint32_t)p.pix * p.atom_y * 2;  // one N atom box
+  const uint32_t a_bytes = ax_bytes * p.atoms_per_mtile;  // pix * 128 channels
   const uint32_t n_atoms = p.bn / p.atom_y;
   const uint32_t b_bytes = ay_bytes * n_atoms;
   const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -483,8 +479,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     mbar_init(tfull0, 1);
     fence_barrier_init();
   }
+  const uint32_t tmem_cols = p.bn <= 32 ? 32u : (p.bn <= 64 ? 64u : (p.bn <= 128 ? 128u : 256u));
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -551,6 +548,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     const uint64_t ap = make_smem_desc(0, ax_bytes, 8 * swz_x, swz_x), bp = make_smem_desc(0, ay_bytes, 8 * swz_y, swz_y);
     const uint32_t a_hi = (uint32_t)(ap >> 32), b_hi = (uint32_t)(bp >> 32);
     const uint32_t kx = (16 * swz_x) >> 4, ky = (16 * swz_y) >> 4;  // 16 pixel rows per UMMA K step
+    const int ksteps = p.pix >> 4;
     uint32_t stage = 0, phase = 0;
     for (int pt = pt_begin; pt < pt_end; ++pt) {
       mbar_wait(full0 + 8 * stage, phase);
@@ -558,8 +556,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
       if (elect_one()) {
         const uint32_t sa = base + stage * stage_bytes;
         const uint32_t a_lo = (uint32_t)ap + (sa >> 4), b_lo = (uint32_t)bp + ((sa + a_bytes) >> 4);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // 128 pixels = 8 UMMA K-steps of 16 rows
+#pragma unroll 4
+        for (int k = 0; k < ksteps; ++k)  // pix pixels = pix / 16 UMMA K-steps of 16 rows
           umma_bf16_lohi(tmem_base, a_lo + k * kx, a_hi, b_lo + k * ky, b_hi, idesc, (uint32_t)((pt != pt_begin) | (k != 0)));
         umma_commit(empty0 + 8 * stage);
         if (pt == pt_end - 1) umma_commit(tfull0);
@@ -602,23 +600,27 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
-static bool spatial_tile(int h, int w, int* th, int* tw) {
-  if (w >= 128) {
-    if (w % 128) return false;
-    *tw = 128;
+static bool spatial_tile(int h, int w, int* th, int* tw, int pix = 128) {
+  if (w >= pix) {
+    if (w % pix) return false;
+    *tw = pix;
     *th = 1;
     return true;
   }
   if (w < 8 || (w & (w - 1))) return false;
   *tw = w;
-  *th = 128 / w;
+  *th = pix / w;
   return h % *th == 0;
+}
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
 }
 static int ilog2(int v) {
   int l = 0;
@@ -799,7 +801,13 @@ static int conv_tc_impl(const xv2_tc_conv* q, const void* src0, const void* src1
   else if (q->c0 % 32 == 0 && q->c1 % 32 == 0 && cg % 32 == 0) bk = 32;
   // transposed conv with the TMA-store epilogue: an N tile may span both kw taps of one kh (a contiguous output row segment)
   const bool convt_wide = convt && q->out_dtype == XV2_BF16 && !bias && (q->ldo == 0 || q->ldo == q->k);
-  const int bn = pick_bn(convt ? (convt_wide ? 2 * q->k : q->k) : kg);
+  // ... or all four taps when they fit one accumulator (k <= 64): the input tile is then fetched once instead of twice
+  int convt_n = convt_wide ? 2 * q->k : q->k;
+  if (convt_wide && 4 * q->k <= 256 && q->k % 16 == 0) {
+    const int sc = (4 * q->k > 64 && (4 * q->k) % 64 == 0) ? 64 : 32;  // staged block (see store_c below) must stay inside one kh
+    if ((2 * q->k) % sc == 0) convt_n = 4 * q->k;
+  }
+  const int bn = pick_bn(convt ? convt_n : kg);
   if (!bk || !bn || (q->out_dtype != XV2_BF16 && q->out_dtype != XV2_F32)) {
     set_error("conv_tc: channels not eligible (c %d+%d k %d groups %d)", q->c0, q->c1, q->k, groups);
     return XV2_EUNSUPPORTED;
@@ -906,8 +914,13 @@ extern "C" int xv2_wgrad_tc(const xv2_tc_conv* q, const void* src0, const void* 
   }
   const int groups = q->groups < 1 ? 1 : q->groups;
   const bool convt = q->convt == 1;
-  int th, tw;
-  if (!spatial_tile(q->h, q->w, &th, &tw) || (groups > 1 && q->c1) || (convt && (groups != 1 || q->c1))) {
+  // Stage geometry knobs, measured on B200 over the 36 1x1 weight gradients of a config-2 step (profiles/r02_wgrad_tc_variants.txt):
+  // 128-pixel stages, N <= 128, one CTA per SM: 2.16 ms;  XV2_WG_PIX=64 (3 stages of 32 KB, two CTAs per SM so that one CTA's
+  // prologue / atomic epilogue hides behind the other's main loop): 2.35 ms;  XV2_WG_PIX=64 XV2_WG_BN=256: 2.46 ms.
+  static const int pix_pref = env_int("XV2_WG_PIX", 128), bn_max = env_int("XV2_WG_BN", 128);
+  int th, tw, pix = pix_pref == 128 ? 128 : 64;
+  if (!spatial_tile(q->h, q->w, &th, &tw, pix)) pix = 128;
+  if (!spatial_tile(q->h, q->w, &th, &tw, pix) || (groups > 1 && q->c1) || (convt && (groups != 1 || q->c1))) {
     set_error("wgrad_tc: shape not eligible (h %d w %d)", q->h, q->w);
     return XV2_EUNSUPPORTED;
   }
@@ -936,7 +949,7 @@ extern "C" int xv2_wgrad_tc(const xv2_tc_conv* q, const void* src0, const void* 
     return XV2_EUNSUPPORTED;
   }
   int bn = 0;
-  for (int cand = 128; cand >= 32; cand -= 32)
+  for (int cand = (bn_max == 256 ? 256 : 128); cand >= 32; cand -= 32)
     if (kg % cand == 0 && cand % atom_y == 0) {
       bn = cand;
       break;
@@ -980,6 +993,7 @@ extern "C" int xv2_wgrad_tc(const xv2_tc_conv* q, const void* src0, const void* 
   p.bn = bn;
   p.gather2x2 = convt ? 1 : 0;
   p.ctot = cg;
+  p.pix = pix;
   p.dw = dw;
   const long long units = (long long)p.m_tiles * p.n_tiles * groups;
   long long splits = (2LL * g_num_sms + units - 1) / units;
@@ -989,9 +1003,10 @@ extern "C" int xv2_wgrad_tc(const xv2_tc_conv* q, const void* src0, const void* 
   const int per = (p.pix_tiles + (int)splits - 1) / (int)splits;
   splits = (p.pix_tiles + per - 1) / per;
   p.splits = (int)splits;
-  const uint32_t stage_bytes = 128u * 128 * 2 + 128u * bn * 2;
+  const uint32_t stage_bytes = (uint32_t)pix * 128 * 2 + (uint32_t)pix * bn * 2;
   int stages = (int)(kSmemBudget / stage_bytes);
   if (stages > 4) stages = 4;
+  if (pix == 64 && bn <= 128 && stages > 3) stages = 3;  // <= 96 KB + barriers: two CTAs per SM
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
   cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -3,6 +3,7 @@
 // pools (unet.py:52).
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace xv2 {
 
@@ -193,6 +194,74 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(PoolGeom g, const T* _
   }
 }
 
+// 3x3 / stride 2 / pad 1 backward on even-sized images, one thread per 2x2 input quad and channel vector: the quad
+// (2a..2a+1, 2b..2b+1) is reached by the windows (a..a+1, b..b+1) only, so 4 dy loads serve 4 dx stores (the per-pixel gather
+// above re-reads every dy element 2.25 times from 4x as many threads).  Same accumulation order as the generic kernels.
+template <typename T, int VEC, bool MAX>
+__global__ void __launch_bounds__(256) pool3s2_bwd_quad_kernel(PoolGeom g, const uint8_t* __restrict__ idx, const T* __restrict__ dy,
+                                                               T* __restrict__ dx) {
+  const int cv = g.c / VEC;
+  const int rowsz = g.ow * cv;
+  const int nb = blockIdx.y / g.oh, a = blockIdx.y - nb * g.oh;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowsz; i += gridDim.x * blockDim.x) {
+    const int b = i / cv, cvi = i - b * cv;
+    float acc[4][VEC];  // quad pixel q = 2 * dr + dc
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[q][j] = 0.f;
+#pragma unroll
+    for (int wr = 0; wr < 2; ++wr) {
+#pragma unroll
+      for (int wc = 0; wc < 2; ++wc) {
+        const int oh = a + wr, ow = b + wc;
+        if (oh >= g.oh || ow >= g.ow) continue;
+        const long long o = (((long long)nb * g.oh + oh) * g.ow + ow) * g.c + cvi * VEC;
+        float d[VEC];
+        pldv<T, VEC>(dy + o, d);
+        uint32_t pk[2] = {0u, 0u};
+        float inv = 0.f;
+        if constexpr (MAX) {
+          if constexpr (VEC == 8) {
+            const uint2 v = *reinterpret_cast<const uint2*>(idx + o);
+            pk[0] = v.x;
+            pk[1] = v.y;
+          } else {
+            pk[0] = *reinterpret_cast<const uint32_t*>(idx + o);
+          }
+        } else {
+          inv = 1.0f / avg_divisor(g, oh, ow, 3, 2);
+        }
+        // window (oh, ow) covers input rows 2 oh - 1 .. 2 oh + 1: quad row dr (input row 2 a + dr) sits at window row 2 (a - oh) + dr + 1
+#pragma unroll
+        for (int dr = 0; dr < 2; ++dr) {
+          const int r = dr + 1 - 2 * wr;
+          if (r < 0) continue;
+#pragma unroll
+          for (int dc = 0; dc < 2; ++dc) {
+            const int sx = dc + 1 - 2 * wc;
+            if (sx < 0) continue;
+            const int q = 2 * dr + dc;
+            if constexpr (MAX) {
+              const uint32_t mine = (uint32_t)(r * 3 + sx);
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) acc[q][j] += ((pk[j >> 2] >> (8 * (j & 3))) & 0xFFu) == mine ? d[j] : 0.f;
+            } else {
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) acc[q][j] = fmaf(d[j], inv, acc[q][j]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+      for (int dc = 0; dc < 2; ++dc)
+        pstv<T, VEC>(dx + (((long long)nb * g.h + 2 * a + dr) * g.w + 2 * b + dc) * g.c + cvi * VEC, acc[2 * dr + dc]);
+  }
+}
+
 static int pool_blocks(long long total) {
   long long b = cdiv(total, 256);
   if (b > 16 * kNumSMs) b = 16 * kNumSMs;
@@ -219,6 +288,30 @@ using namespace xv2;
     XV2_LAUNCH_CHECK();                                                                         \
   } while (0)
 
+// quad kernel eligibility: 3x3 / 2 / 1 on even images with vectorised channels
+static bool quad_ok(int h, int w, int c, int oh, int ow, int k, int stride, int pad, int dtype) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("XV2_NO_POOL_QUAD");
+    enabled = (e && e[0] == '1') ? 0 : 1;
+  }
+  const int vecw = dtype == XV2_BF16 ? 8 : 4;
+  return enabled && k == 3 && stride == 2 && pad == 1 && h == 2 * oh && w == 2 * ow && c % vecw == 0;
+}
+template <bool MAX>
+static int launch_quad(const PoolGeom& g, const uint8_t* idx, const void* dy, void* dx, int dtype, void* stream) {
+  const int vecw = dtype == XV2_BF16 ? 8 : 4;
+  const long long rowsz = (long long)g.ow * (g.c / vecw);
+  XV2_REQUIRE((long long)g.n * g.oh <= 65535, "pool: tensor too large for the 2-D grid");
+  const dim3 grid((unsigned)std::min<long long>(cdiv(rowsz, 256), 64), (unsigned)(g.n * g.oh));
+  if (dtype == XV2_BF16)
+    pool3s2_bwd_quad_kernel<__nv_bfloat16, 8, MAX><<<grid, 256, 0, as_stream(stream)>>>(g, idx, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx);
+  else
+    pool3s2_bwd_quad_kernel<float, 4, MAX><<<grid, 256, 0, as_stream(stream)>>>(g, idx, (const float*)dy, (float*)dx);
+  XV2_LAUNCH_CHECK();
+  return XV2_OK;
+}
+
 extern "C" int xv2_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t n, int32_t h, int32_t w, int32_t c,
                                int32_t oh, int32_t ow, int32_t k, int32_t stride, int32_t pad, int32_t dtype,
                                void* stream) {
@@ -233,6 +326,7 @@ extern "C" int xv2_maxpool_bwd(const uint8_t* idx, const void* dy, void* dx, int
   XV2_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0 && k > 0 && stride > 0, "maxpool: bad shape");
   XV2_REQUIRE(idx != nullptr, "maxpool_bwd: index map missing");
   PoolGeom g{n, h, w, c, oh, ow, k, stride, pad, 0};
+  if (quad_ok(h, w, c, oh, ow, k, stride, pad, dtype)) return launch_quad<true>(g, idx, dy, dx, dtype, stream);
   XV2_POOL_LAUNCH(maxpool_bwd_kernel, n, h, w, g, idx, (const T*)dy, (T*)dx);
   return XV2_OK;
 }
@@ -249,6 +343,7 @@ extern "C" int xv2_avgpool_bwd(const void* dy, void* dx, int32_t n, int32_t h, i
                                int32_t dtype, void* stream) {
   XV2_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0 && k > 0 && stride > 0, "avgpool: bad shape");
   PoolGeom g{n, h, w, c, oh, ow, k, stride, pad, count_include_pad};
+  if (quad_ok(h, w, c, oh, ow, k, stride, pad, dtype)) return launch_quad<false>(g, nullptr, dy, dx, dtype, stream);
   XV2_POOL_LAUNCH(avgpool_bwd_kernel, n, h, w, g, (const T*)dy, (T*)dx);
   return XV2_OK;
 }

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "xv2_bn_apply": [P, P, P, I64, I32, I32, P, P, I32, P],
     "xv2_bn_train_apply": [P, P, P, I64, I32, I32, P, I64, P, P, P, P, F, F, P, I32, P],
     "xv2_bn_bwd_reduce": [P, P, P, I64, I32, I32, P, P, P, P, I32, P, P],
+    "xv2_bn_bwd_reduce_du": [P, P, P, P, P, I64, I32, I32, P, P, P, P, I32, P, P],
     "xv2_bn_bwd_apply": [P, P, P, P, P, I64, I32, I32, P, P, P, P, P, I32, P, I64, P, P, I32, P],
     "xv2_maxpool_fwd": [P, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
     "xv2_maxpool_bwd": [P, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],

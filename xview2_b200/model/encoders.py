@@ -68,11 +68,12 @@ class SplAtBottleneck(nn.Module):
             self.downsample = None
 
     def forward(self, x):
+        # identity shortcut: x feeds conv1 and the shortcut only -- their two gradients meet inside the producer's BN backward
+        x, res = ops.fork(x) if self.downsample is None else (x, x)
         out = ops.conv_bn_act(x, self.conv1, self.bn1, ACT_RELU)
         out = self.conv2(out)
         if self.avd_stride:
             out = ops.avg_pool2d(out, 3, self.avd_stride, 1)
-        res = x
         if self.downsample is not None:
             if self.down_pool > 1:
                 res = ops.avg_pool2d(res, self.down_pool, self.down_pool, 0, ceil_mode=True, count_include_pad=False)
@@ -181,9 +182,9 @@ class Bottleneck(nn.Module):
             self.downsample = None
 
     def forward(self, x):
+        x, res = ops.fork(x) if self.downsample is None else (x, x)
         out = ops.conv_bn_act(x, self.conv1, self.bn1, ACT_RELU)
         out = ops.conv_bn_act(out, self.conv2, self.bn2, ACT_RELU)
-        res = x
         if self.downsample is not None:
             res = ops.conv_bn_act(x, _sub(self.downsample, "0"), _sub(self.downsample, "1"), ACT_NONE)
         return ops.conv_bn_act(out, self.conv3, self.bn3, ACT_RELU, residual=res)

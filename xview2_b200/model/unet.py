@@ -95,16 +95,18 @@ class UNetTemplate(nn.Module):
                 self.enc_chn, self.dilation, args.attention, self.no_skip, args.dec_interp)
 
     def encode(self, data):
-        enc1 = self.enc_l1(data)
-        enc2 = self.enc_l2(enc1)
-        enc3 = self.enc_l3(enc2)
-        enc4 = self.enc_l4(enc3)
+        # every stage output feeds the next stage AND the decoder (skip): ops.fork keeps autograd from summing the two gradient
+        # parts in a pass of its own -- the stage's last BatchNorm backward adds them while it streams (s*: the skip aliases)
+        enc1, s1 = ops.fork(self.enc_l1(data))
+        enc2, s2 = ops.fork(self.enc_l2(enc1))
+        enc3, s3 = ops.fork(self.enc_l3(enc2))
+        enc4, s4 = ops.fork(self.enc_l4(enc3))
         enc5 = self.enc_l5(enc4)
         if self.use_ppm:      # unet.py:144-147
             enc5 = self.ppm(enc5)
         elif self.use_aspp:
             enc5 = self.aspp(enc5)
-        return [enc1, enc2, enc3, enc4, enc5]
+        return [s1, s2, s3, s4, enc5]
 
     def forward(self, data, defer_tail=False):
         encs = self.encode(data)

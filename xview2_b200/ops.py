@@ -189,6 +189,7 @@ class _OnSide:
 def sync_side_streams():
     """The current stream waits for every weight gradient issued on a side stream (called before the gradient all-reduce /
     optimizer step / anything that reads .grad)."""
+    check_pending_addends()
     cur = torch.cuda.current_stream() if torch.cuda.is_available() else None
     for st in list(_side_dirty):
         cur.wait_stream(st)
@@ -215,6 +216,7 @@ _zarena = {}
 
 
 def new_step_scratch(device):
+    check_pending_addends()
     st = _zarena.get(device.index)
     if st is None:
         _zarena[device.index] = [torch.zeros(_ZARENA_BYTES, dtype=torch.uint8, device=device), 0]
@@ -512,17 +514,35 @@ class _BatchNormAct(torch.autograd.Function):
     def backward(ctx, dy):
         x, residual, gamma, coef = ctx.saved_tensors
         training, act = ctx.cfg
+        dy2 = _pop_addend(dy)  # second part of the gradient (ops.fork), summed inside the reduce kernel
         dy = nhwc(dy)
         n, c, h, w = x.shape
         pixels = n * h * w
         mean, invstd, scale, shift = coef[0], coef[1], coef[2], coef[3]
         dt = dtype_code(x)
         red = zeros_scratch(2 * c, torch.float64, x.device)
+        gg, gb = ctx.flat_grads
+        want_dres = residual is not None and ctx.needs_input_grad[1]
+        if training and (residual is not None or dy2 is not None) and dt == BF16:
+            # residual join: pass 1 writes du = (dy [+ dy2]) * act'(u) once -- it IS the shortcut's gradient -- and pass 2 reads
+            # (du, x) only: 7 streaming passes (8 with dy2) instead of 8 plus autograd's 3-pass accumulation of dy + dy2
+            du = torch.empty_like(x)
+            rc = call("xv2_bn_bwd_reduce_du", ptr(dy), ptr(dy2), ptr(x), ptr(residual), ptr(du), pixels, c, dt, ptr(scale),
+                      ptr(shift), ptr(mean), ptr(invstd), act, ptr(red), allow_unsupported=True)
+            if rc == 0:
+                dx = torch.empty_like(x)
+                dgb = None if gg is not None else torch.empty(2, c, dtype=torch.float32, device=x.device)
+                call("xv2_bn_bwd_apply", ptr(du), ptr(x), None, ptr(dx), None, pixels, c, dt, ptr(scale), ptr(shift), ptr(mean),
+                     ptr(invstd), ptr(gamma), ACT_NONE, ptr(red), pixels, ptr(gg if dgb is None else dgb[0]),
+                     ptr(gb if dgb is None else dgb[1]), 1 if dgb is None else 0)
+                return (dx, (du if want_dres else None), None if dgb is None else dgb[0], None if dgb is None else dgb[1],
+                        None, None, None, None, None, None, None)
+        if dy2 is not None:
+            dy = nhwc(dy + nhwc(dy2))
         call("xv2_bn_bwd_reduce", ptr(dy), ptr(x), ptr(residual), pixels, c, dt, ptr(scale), ptr(shift), ptr(mean),
              ptr(invstd), act, ptr(red))
         dx = torch.empty_like(x)
-        dres = torch.empty_like(x) if residual is not None and ctx.needs_input_grad[1] else None
-        gg, gb = ctx.flat_grads
+        dres = torch.empty_like(x) if want_dres else None
         if training and gg is not None:
             # the parameters' own gradient slots in the flat buffer (zeroed once per step): the kernel adds to them, autograd
             # launches no accumulation kernel for gamma / beta
@@ -539,13 +559,60 @@ class _BatchNormAct(torch.autograd.Function):
         return dx, dres, dgb[0], dgb[1], None, None, None, None, None, None, None
 
 
+# A block output consumed twice by the next residual block (its conv1 and its shortcut) would get its two gradients summed by an
+# autograd accumulation kernel (3 passes over the activation).  ops.fork splits the tensor into two aliases; in backward it
+# passes the conv1 part on and parks the shortcut part here, keyed by the storage it travels with, for the producer's
+# _BatchNormAct.backward to pick up (xv2_bn_bwd_reduce_du sums them while it streams).  check_pending_addends() -- run at every
+# step boundary -- fails loudly if a parked part was never collected.
+FORK_GRADS = _os.environ.get("XV2_NO_FORK", "0") != "1"
+_pending_addends = {}
+
+
+def _pop_addend(dy):
+    hit = _pending_addends.pop(dy.data_ptr(), None) if _pending_addends else None
+    return None if hit is None else hit[1]
+
+
+def check_pending_addends():
+    if _pending_addends:
+        n = len(_pending_addends)
+        _pending_addends.clear()
+        raise RuntimeError(f"ops.fork: {n} parked gradient part(s) were never consumed by a BatchNorm backward")
+
+
+class _Fork(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, da, db):
+        if da is None or db is None:
+            return da if db is None else db
+        da = nhwc(da)
+        _pending_addends[da.data_ptr()] = (da, nhwc(db))  # holding `da` keeps its storage from being reused while parked
+        return da
+
+
+def fork(x):
+    """Two aliases of a train-mode batch_norm_act output that has NO other consumer (a block output feeding the next block's
+    conv1 and shortcut; an encoder stage output feeding the next stage and the decoder); anything else gets (x, x) and
+    autograd's own accumulation."""
+    if FORK_GRADS and getattr(x, "_xv2_forkable", False) and torch.is_grad_enabled() and x.requires_grad:
+        return _Fork.apply(x)
+    return x, x
+
+
 def batch_norm_act(x, bn, act=ACT_NONE, residual=None, stats=None):
     """Applies the nn.BatchNorm2d module `bn` (its parameters / buffers / training flag) followed by `act`."""
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     use_batch = bn.training or not bn.track_running_stats
-    return _BatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch,
-                               bn.momentum if bn.momentum is not None else 0.1, bn.eps, act, stats if use_batch else None)
+    y = _BatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch,
+                            bn.momentum if bn.momentum is not None else 0.1, bn.eps, act, stats if use_batch else None)
+    if use_batch and y.dtype == torch.bfloat16:
+        y._xv2_forkable = True  # see ops.fork
+    return y
 
 
 def _eval_coeffs(bn):
