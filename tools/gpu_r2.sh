@@ -15,6 +15,7 @@ for s in $STAGES; do
     smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log ;;
     bench) timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -c 2500 gpurun_out/bench_c2.json; tail -5 gpurun_out/bench_c2.err ;;
     bench_quick) timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-library-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; python tools/show_bench.py gpurun_out/bench_quick.json; tail -5 gpurun_out/bench_quick.err ;;
+    bench_pdl) XV2_PDL=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-library-baseline > gpurun_out/bench_pdl.json 2> gpurun_out/bench_pdl.err; python tools/show_bench.py gpurun_out/bench_pdl.json | head -8; tail -5 gpurun_out/bench_pdl.err ;;
     bench_c3|bench_c4|bench_c5) c=${s#bench_}; timeout 1500 python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; python tools/show_bench.py gpurun_out/bench_$c.json; tail -5 gpurun_out/bench_$c.err ;;
     ref) timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 1200 gpurun_out/bench_ref.json ;;
     layers) timeout 600 python tools/layer_profile.py > gpurun_out/layers.txt 2> gpurun_out/layers.err; head -3 gpurun_out/layers.txt; tail -3 gpurun_out/layers.err ;;
@@ -24,9 +25,9 @@ for s in $STAGES; do
         --profile-from-start off --csv --log-file gpurun_out/traffic.csv python tools/layer_profile.py --ncu > gpurun_out/traffic.log 2>&1; wc -l gpurun_out/traffic.csv ;;
     ncu_zoo) # one --set full row per kernel family at its C2 shape; the report stays on the box, the CSV comes back
         timeout 1200 $NCU --set full --clock-control none --profile-from-start off --kernel-name-base demangled -k regex:"xv2::" -c ${ZOO_COUNT:-120} \
-          -f -o /tmp/prof_zoo python tools/kernel_zoo.py ${ZOO_ARGS:-} > gpurun_out/ncu_zoo.log 2>&1; tail -3 gpurun_out/ncu_zoo.log
-        $NCU -i /tmp/prof_zoo.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size,smsp__inst_executed.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,lts__t_bytes.sum > gpurun_out/ncu_zoo.csv 2>/dev/null; wc -l gpurun_out/ncu_zoo.csv
-        $NCU -i /tmp/prof_zoo.ncu-rep --page details --csv --section WarpStateStats --section SpeedOfLight > gpurun_out/ncu_zoo_details.csv 2>/dev/null; wc -c gpurun_out/ncu_zoo_details.csv ;;
+          -f -o /tmp/prof_zoo python tools/kernel_zoo.py ${ZOO_ARGS:-} > gpurun_out/ncu_zoo${ZOO_TAG:-}.log 2>&1; tail -3 gpurun_out/ncu_zoo${ZOO_TAG:-}.log
+        $NCU -i /tmp/prof_zoo.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size,smsp__inst_executed.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,lts__t_bytes.sum > gpurun_out/ncu_zoo${ZOO_TAG:-}.csv 2>/dev/null; wc -l gpurun_out/ncu_zoo${ZOO_TAG:-}.csv
+        $NCU -i /tmp/prof_zoo.ncu-rep --page details --csv --section WarpStateStats --section SpeedOfLight > gpurun_out/ncu_zoo${ZOO_TAG:-}_details.csv 2>/dev/null; wc -c gpurun_out/ncu_zoo${ZOO_TAG:-}_details.csv ;;
     scale2|scale4|scale8) n=${s#scale}; for c in ${CFGS:-c2}; do
         timeout -k 10 ${SCALE_TIMEOUT:-240} $TR --nproc-per-node $n --master-port 295$n bench.py --config $c --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_${c}_n$n${TAG:-}.json 2> gpurun_out/scale_${c}_n$n${TAG:-}.err
         python tools/show_bench.py gpurun_out/scale_${c}_n$n${TAG:-}.json | head -3; tail -3 gpurun_out/scale_${c}_n$n${TAG:-}.err | cut -c1-300; done ;;

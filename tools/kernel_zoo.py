@@ -16,6 +16,7 @@ from xview2_b200.lib import ACT_LRELU, ACT_RELU
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--list", action="store_true")
+ap.add_argument("--only", default="", help="comma-separated substrings: run only the cases whose name contains one of them")
 a = ap.parse_args()
 torch.cuda.set_device(0)
 lib.init(0)
@@ -93,6 +94,18 @@ for name, c, h, res in (("bn lrelu c32 @1024", 32, 1024, False), ("bn relu+res c
         y = ops.batch_norm_act(z, b, ACT_RELU if res else ACT_LRELU, r)
         y.backward(torch.ones_like(y))
     cases.append((name, run))
+# residual join whose gradient arrives in two parts (ops.fork): xv2_bn_bwd_reduce_du sums them while it streams
+zf, bf_, rf = act(8, 256, 256, 256), bn(256), act(8, 256, 256, 256)
+gf = [torch.ones(8, 256, 256, 256, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=CL) for _ in range(2)]
+
+
+def bn_fork():
+    ya, yb = ops.fork(ops.batch_norm_act(zf, bf_, ACT_RELU, rf))
+    torch.autograd.backward([ya, yb], gf)
+    ops.check_pending_addends()
+
+
+cases.append(("bn relu+res c256 @256, two-part gradient (fork)", bn_fork))
 # fused split attention (bn0 + relu folded in)
 from xview2_b200.model.encoders import SplAtConv2d, _init_resnest
 sp = SplAtConv2d(64, 1)
@@ -143,6 +156,9 @@ logits4 = torch.randn(8, 2, 1024, 1024, device="cuda").contiguous(memory_format=
 cnt = torch.zeros(3, dtype=torch.int64, device="cuda")
 cases.append(("f1_update + argmax map 8 x 1024^2", lambda: ops.f1_update(logits4, labels, 2, cnt, torch.empty(8, 1024, 1024, dtype=torch.uint8, device="cuda"))))
 
+if a.only:
+    keys = [k for k in a.only.split(",") if k]
+    cases = [(n, f) for n, f in cases if any(k in n for k in keys)]
 if a.list:
     for n, _ in cases:
         print(n)

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(288, 2) bn_stream_kernel(const BnStreamParams 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long nchunks = (p.elems + kChunkElems - 1) / kChunkElems;
   const uint32_t S = (uint32_t)p.stages;
+  pdl_trigger();
 
   if (tid == 0) {
     for (uint32_t s = 0; s < S; ++s) {
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(288, 2) bn_stream_kernel(const BnStreamParams 
     }
     fence_barrier_init();
   }
+  pdl_wait();  // the statistics / coefficients read below come from the preceding kernels
   if (MODE == BN_APPLY && p.fin_stats != nullptr && blockIdx.x == 0) {
     // fused finalize: block 0 publishes the saved coefficients and updates the running statistics
     for (int i = tid; i < p.c; i += blockDim.x) {
@@ -309,7 +311,11 @@ template <int MODE> static int launch_stream(BnStreamParams& p, void* stream) {
   const long long nchunks = (p.elems + kChunkElems - 1) / kChunkElems;
   long long grid = 2LL * kNumSMs;
   if (grid > nchunks) grid = nchunks;
-  bn_stream_kernel<MODE><<<(unsigned)grid, 288, smem, as_stream(stream)>>>(p);
+  cudaError_t le = launch_pdl(bn_stream_kernel<MODE>, dim3((unsigned)grid), dim3(288), smem, as_stream(stream), p);
+  if (le != cudaSuccess) {
+    set_error("bn_stream: launch: %s", cudaGetErrorString(le));
+    return XV2_ECUDA;
+  }
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 #include "../../include/xv2.h"
 
@@ -35,6 +36,35 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t dtype_size(int dt) { return dt == XV2_BF16 ? 2 : 4; }
 
 constexpr int kNumSMs = 148;
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
+// A training step is ~600 short dependent launches replayed from one CUDA graph; between two of them the GPU idles for the
+// launch latency plus the successor's prologue (barrier init, TMEM allocation, descriptor prefetch, coefficient loads).
+// Kernels launched through launch_pdl() carry cudaLaunchAttributeProgrammaticStreamSerialization: they may be scheduled as soon
+// as every CTA of the predecessor has executed pdl_trigger() (first instruction of our kernels), run their prologue, and then
+// block in pdl_wait() until the predecessor grid has COMPLETED and its writes are visible -- no global memory is touched before
+// pdl_wait().  Under stream capture the edge becomes a programmatic graph dependency.
+// MEASURED (B200, config-2 step replayed from its CUDA graph, profiles/r02_pdl_experiment.txt): 35.12 ms with the attribute on
+// the conv / wgrad / BN / split-attention kernels vs 33.12 ms without -- the programmatic edges cost more than the ~2 us
+// bubbles they hide -- so the attribute is OFF unless XV2_PDL=1 (griddepcontrol.* are no-ops for a plain launch).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- scalar / vector load-store with conversion to fp32 ---------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T v);

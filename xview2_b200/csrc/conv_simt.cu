@@ -3,6 +3,7 @@
 // (3-channel strided stem, torchvision-ResNet strided convs, the tiny SplAt FCs) and as the on-device cross-check of
 // the tensor-core kernels.  Replaces cuDNN calls reached from layers.py:83,92,71,180 and unet.py:52.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace xv2 {
 
@@ -12,6 +13,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("XV2_PDL");  // opt-in: measured SLOWER on B200 inside the captured step (see common.cuh)
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 struct GatherGeom {

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int epi_warps = p.bn >= 64 ? 8 : 4;
   const uint32_t tmem_cols = p.bn <= 16 ? 32u : (p.bn <= 32 ? 64u : (p.bn <= 64 ? 128u : 256u));  // 2 accumulators
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.map_a0);
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(320, 1) conv_strip_kernel(const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   const long long lo0 = p.rows_total * blockIdx.x / gridDim.x;
   const long long hi0 = p.rows_total * (blockIdx.x + 1) / gridDim.x;
@@ -384,7 +386,7 @@ int conv_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1, 
 #define XV2_STRIP_LAUNCH(BKV, CH)                                                                                        \
   do {                                                                                                                   \
     e = cudaFuncSetAttribute(conv_strip_kernel<BKV, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-    if (e == cudaSuccess) conv_strip_kernel<BKV, CH><<<(unsigned)grid, 320, smem, as_stream(stream)>>>(p);               \
+    if (e == cudaSuccess) e = launch_pdl(conv_strip_kernel<BKV, CH>, dim3((unsigned)grid), dim3(320), smem, as_stream(stream), p); \
   } while (0)
   if (bk == 32) XV2_STRIP_LAUNCH(32, 1);
   else if (chunks == 1) XV2_STRIP_LAUNCH(64, 1);

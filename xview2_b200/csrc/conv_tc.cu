@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   const uint32_t stats_sm = stage_out0 + 2 * p.out_bufs * 16384;   // float [2 * k_total] when p.stats
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int epi_warps = p.tma_store ? 8 : 4;
+  pdl_trigger();
 
   if (p.stats) {
     for (int i = threadIdx.x; i < 2 * p.k_total; i += blockDim.x)
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // everything above touched only shared memory, TMEM and the kernel parameters
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.groups;
   const int kb_per_tap = p.kb0 + p.kb1;
@@ -468,6 +470,7 @@ __global__ void __launch_bounds__(192, 2) wgrad_tc_kernel(const __grid_constant_
   const uint32_t full0 = bar_base, empty0 = bar_base + 64, tfull0 = bar_base + 128;
   const uint32_t tmem_slot = bar_base + 160;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.map_x0);
@@ -489,6 +492,7 @@ __global__ void __launch_bounds__(192, 2) wgrad_tc_kernel(const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   // one work unit per CTA: (n_tile, m_tile, group, split)
   int u = blockIdx.x;
@@ -890,13 +894,13 @@ static int conv_tc_impl(const xv2_tc_conv* q, const void* src0, const void* src1
   cudaError_t e;
   if (bk == 64) {
     e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_tc_kernel<64><<<grid, 320, smem, st>>>(p);
+    if (e == cudaSuccess) e = launch_pdl(conv_tc_kernel<64>, dim3(grid), dim3(320), smem, st, p);
   } else {
     e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_tc_kernel<32><<<grid, 320, smem, st>>>(p);
+    if (e == cudaSuccess) e = launch_pdl(conv_tc_kernel<32>, dim3(grid), dim3(320), smem, st, p);
   }
   if (e != cudaSuccess) {
-    set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    set_error("conv_tc: launch: %s", cudaGetErrorString(e));
     return XV2_ECUDA;
   }
   XV2_LAUNCH_CHECK();
@@ -1014,7 +1018,11 @@ extern "C" int xv2_wgrad_tc(const xv2_tc_conv* q, const void* src0, const void* 
     set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return XV2_ECUDA;
   }
-  wgrad_tc_kernel<<<(unsigned)(units * splits), 192, smem, as_stream(stream)>>>(p);
+  e = launch_pdl(wgrad_tc_kernel, dim3((unsigned)(units * splits)), dim3(192), smem, as_stream(stream), p);
+  if (e != cudaSuccess) {
+    set_error("wgrad_tc: launch: %s", cudaGetErrorString(e));
+    return XV2_ECUDA;
+  }
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }

@@ -376,6 +376,8 @@ __global__ void __launch_bounds__(256) sa_fc1_bn_relu_kernel(const float* __rest
                                                              float* __restrict__ rvar, float momentum, float eps, int training,
                                                              float* __restrict__ z1, float* __restrict__ a1,
                                                              float* __restrict__ coef, int n, int c, int inter) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= inter) return;
@@ -424,6 +426,8 @@ __global__ void __launch_bounds__(256) sa_fc1_bn_relu_kernel(const float* __rest
 __global__ void __launch_bounds__(256) sa_fc2_rsoftmax_kernel(const float* __restrict__ a1, const float* __restrict__ w2,
                                                               const float* __restrict__ b2, float* __restrict__ att, int n,
                                                               int c, int inter) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= c) return;
@@ -446,6 +450,8 @@ __global__ void __launch_bounds__(256) sa_bwd_fc2_kernel(const float* __restrict
                                                          const float* __restrict__ a1, float* __restrict__ dz2,
                                                          float* __restrict__ dw2, float* __restrict__ db2, int n, int c,
                                                          int inter) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= c) return;
@@ -487,6 +493,8 @@ __global__ void __launch_bounds__(256) sa_bwd_bn_fc1_kernel(const float* __restr
                                                             int training, float* __restrict__ dz1, float* __restrict__ dw1,
                                                             float* __restrict__ db1, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int n, int c, int inter) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= inter) return;
@@ -527,6 +535,8 @@ __global__ void __launch_bounds__(256) sa_bwd_bn_fc1_kernel(const float* __restr
 // backward 3: dgap[n][c] = sum_j dz1[n][j] w1t[c][j]  (w1t = fc1's weight transposed: [c][inter]); warp per channel c
 __global__ void __launch_bounds__(256) sa_bwd_gap_kernel(const float* __restrict__ dz1, const float* __restrict__ w1t,
                                                          float* __restrict__ dgap, int n, int c, int inter) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int cc = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (cc >= c) return;
@@ -545,9 +555,9 @@ extern "C" int xv2_splat_fc_fwd(const float* gap, const float* w1, const float* 
               n, c, inter);
   XV2_REQUIRE(training == 0 || n > 1, "Expected more than 1 value per channel when training");
   XV2_REQUIRE(training != 0 || (running_mean && running_var), "splat_fc_fwd: eval mode needs running statistics");
-  sa_fc1_bn_relu_kernel<<<(inter + 7) / 8, 256, 0, as_stream(stream)>>>(gap, w1, b1, gamma, beta, running_mean, running_var, momentum,
+  launch_pdl(sa_fc1_bn_relu_kernel, dim3((inter + 7) / 8), dim3(256), 0, as_stream(stream), gap, w1, b1, gamma, beta, running_mean, running_var, momentum,
                                                                         eps, training, z1, a1, coef, n, c, inter);
-  sa_fc2_rsoftmax_kernel<<<(c + 7) / 8, 256, 0, as_stream(stream)>>>(a1, w2, b2, att, n, c, inter);
+  launch_pdl(sa_fc2_rsoftmax_kernel, dim3((c + 7) / 8), dim3(256), 0, as_stream(stream), a1, w2, b2, att, n, c, inter);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }
@@ -560,10 +570,10 @@ extern "C" int xv2_splat_fc_bwd(const float* att, const float* datt, const float
                   dgap,
               "splat_fc_bwd: null argument");
   XV2_REQUIRE(n >= 1 && n <= kSaMaxN && c % 4 == 0 && inter % 4 == 0, "splat_fc_bwd: n <= 32, channels multiples of 4");
-  sa_bwd_fc2_kernel<<<(c + 7) / 8, 256, 0, as_stream(stream)>>>(att, datt, a1, dz2, dw2, db2, n, c, inter);
-  sa_bwd_bn_fc1_kernel<<<(inter + 7) / 8, 256, 0, as_stream(stream)>>>(dz2, w2t, z1, coef, gamma, gap, training, dz1, dw1, db1, dgamma,
+  launch_pdl(sa_bwd_fc2_kernel, dim3((c + 7) / 8), dim3(256), 0, as_stream(stream), att, datt, a1, dz2, dw2, db2, n, c, inter);
+  launch_pdl(sa_bwd_bn_fc1_kernel, dim3((inter + 7) / 8), dim3(256), 0, as_stream(stream), dz2, w2t, z1, coef, gamma, gap, training, dz1, dw1, db1, dgamma,
                                                                        dbeta, n, c, inter);
-  sa_bwd_gap_kernel<<<(c + 7) / 8, 256, 0, as_stream(stream)>>>(dz1, w1t, dgap, n, c, inter);
+  launch_pdl(sa_bwd_gap_kernel, dim3((c + 7) / 8), dim3(256), 0, as_stream(stream), dz1, w1t, dgap, n, c, inter);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }

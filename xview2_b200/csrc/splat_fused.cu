@@ -129,6 +129,8 @@ __global__ void __launch_bounds__(256) splat_bn_gap_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(256) splat_bn_combine_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
                                                                const float* __restrict__ shift, const float* __restrict__ att,
                                                                __nv_bfloat16* __restrict__ out, long long hw, int c, SplatMap m) {
+  pdl_trigger();
+  pdl_wait();
   const int cvi = threadIdx.x % m.cvt, lane = threadIdx.x / m.cvt;
   const int ch0 = cvi * 8, nb = blockIdx.y;
   float s0[8], h0[8], s1[8], h1[8], a0[8], a1[8];
@@ -170,6 +172,8 @@ __global__ void __launch_bounds__(256) splat_bn_bwd_partials_kernel(const __nv_b
                                                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                                                     double* __restrict__ part, long long hw, int c, int n,
                                                                     SplatMap m) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sm[256][8];
   const int cvi = threadIdx.x % m.cvt, lane = threadIdx.x / m.cvt;
   const int ch0 = cvi * 8, nb = blockIdx.y;
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(256) splat_bn_bwd_partials_kernel(const __nv_b
 // datt[n][2c] = scale * A2 + shift * A1
 __global__ void splat_bn_bwd_datt_kernel(const double* __restrict__ part, const float* __restrict__ scale,
                                          const float* __restrict__ shift, float* __restrict__ datt, int n, int c2) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * c2) return;
   const int ch = i % c2;
@@ -232,6 +238,8 @@ __global__ void splat_bn_bwd_datt_kernel(const double* __restrict__ part, const 
 __global__ void splat_bn_bwd_red_kernel(const double* __restrict__ part, const float* __restrict__ att,
                                         const float* __restrict__ dgap, const float* __restrict__ mean,
                                         const float* __restrict__ invstd, double* __restrict__ red, int n, int c, float inv_hw) {
+  pdl_trigger();
+  pdl_wait();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   const int c2 = 2 * c;
   if (ch >= c2) return;
@@ -260,6 +268,8 @@ __global__ void __launch_bounds__(256) splat_bn_bwd_apply_kernel(const __nv_bflo
                                                                  __nv_bfloat16* __restrict__ dz, float* __restrict__ dgamma,
                                                                  float* __restrict__ dbeta, int accumulate, long long hw, int c,
                                                                  float inv_hw, float inv_count, SplatMap m) {
+  pdl_trigger();
+  pdl_wait();
   const int c2 = 2 * c;
   if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma != nullptr) {
     for (int i = threadIdx.x; i < c2; i += blockDim.x) {
@@ -355,8 +365,7 @@ extern "C" int xv2_splat_bn_combine(const void* z, const float* scale, const flo
                                     int32_t n, int64_t hw, int32_t c, void* stream) {
   XV2_REQUIRE(z && scale && shift && att && out, "splat_bn_combine: null argument");
   XV2_SPLAT_SHAPE("splat_bn_combine", c / 8)
-  splat_bn_combine_kernel<<<splat_grid(n, hw, m.lanes, 8), 256, 0, as_stream(stream)>>>(
-      (const __nv_bfloat16*)z, scale, shift, att, (__nv_bfloat16*)out, hw, c, m);
+  launch_pdl(splat_bn_combine_kernel, dim3(splat_grid(n, hw, m.lanes, 8)), dim3(256), 0, as_stream(stream), (const __nv_bfloat16*)z, scale, shift, att, (__nv_bfloat16*)out, hw, c, m);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }
@@ -365,8 +374,7 @@ extern "C" int xv2_splat_bn_bwd_partials(const void* z, const void* dout, const 
                                          int32_t n, int64_t hw, int32_t c, void* stream) {
   XV2_REQUIRE(z && dout && scale && shift && part, "splat_bn_bwd_partials: null argument");
   XV2_SPLAT_SHAPE("splat_bn_bwd_partials", 2 * c / 8)
-  splat_bn_bwd_partials_kernel<<<splat_grid(n, hw, m.lanes, 16), 256, 0, as_stream(stream)>>>(
-      (const __nv_bfloat16*)z, (const __nv_bfloat16*)dout, scale, shift, part, hw, c, n, m);
+  launch_pdl(splat_bn_bwd_partials_kernel, dim3(splat_grid(n, hw, m.lanes, 16)), dim3(256), 0, as_stream(stream), (const __nv_bfloat16*)z, (const __nv_bfloat16*)dout, scale, shift, part, hw, c, n, m);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }
@@ -375,7 +383,7 @@ extern "C" int xv2_splat_bn_bwd_datt(const double* part, const float* scale, con
                                      int32_t c, void* stream) {
   XV2_REQUIRE(part && scale && shift && datt && n > 0 && c > 0, "splat_bn_bwd_datt: bad argument");
   const int total = n * 2 * c;
-  splat_bn_bwd_datt_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(part, scale, shift, datt, n, 2 * c);
+  launch_pdl(splat_bn_bwd_datt_kernel, dim3((total + 255) / 256), dim3(256), 0, as_stream(stream), part, scale, shift, datt, n, 2 * c);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }
@@ -383,7 +391,7 @@ extern "C" int xv2_splat_bn_bwd_datt(const double* part, const float* scale, con
 extern "C" int xv2_splat_bn_bwd_red(const double* part, const float* att, const float* dgap, const float* mean,
                                     const float* invstd, double* red, int32_t n, int64_t hw, int32_t c, void* stream) {
   XV2_REQUIRE(part && att && dgap && mean && invstd && red && n > 0 && c > 0 && hw > 0, "splat_bn_bwd_red: bad argument");
-  splat_bn_bwd_red_kernel<<<(2 * c + 127) / 128, 128, 0, as_stream(stream)>>>(part, att, dgap, mean, invstd, red, n, c,
+  launch_pdl(splat_bn_bwd_red_kernel, dim3((2 * c + 127) / 128), dim3(128), 0, as_stream(stream), part, att, dgap, mean, invstd, red, n, c,
                                                                              1.0f / (float)hw);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
@@ -395,8 +403,7 @@ extern "C" int xv2_splat_bn_bwd_apply(const void* z, const void* dout, const flo
                                       int64_t hw, int32_t c, void* stream) {
   XV2_REQUIRE(z && dout && att && dgap && scale && shift && mean && invstd && gamma && red && dz, "splat_bn_bwd_apply: null argument");
   XV2_SPLAT_SHAPE("splat_bn_bwd_apply", 2 * c / 8)
-  splat_bn_bwd_apply_kernel<<<splat_grid(n, hw, m.lanes, 8), 256, 0, as_stream(stream)>>>(
-      (const __nv_bfloat16*)z, (const __nv_bfloat16*)dout, att, dgap, scale, shift, mean, invstd, gamma, red,
+  launch_pdl(splat_bn_bwd_apply_kernel, dim3(splat_grid(n, hw, m.lanes, 8)), dim3(256), 0, as_stream(stream), (const __nv_bfloat16*)z, (const __nv_bfloat16*)dout, att, dgap, scale, shift, mean, invstd, gamma, red,
       (__nv_bfloat16*)dz, dgamma, dbeta, accumulate, hw, c, 1.0f / (float)hw, 1.0f / ((float)n * (float)hw), m);
   XV2_LAUNCH_CHECK();
   return XV2_OK;

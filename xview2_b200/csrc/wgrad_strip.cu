@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_strip_kernel(const __grid_consta
   const uint32_t xfull0 = bar_base, xempty0 = xfull0 + 8 * kWgXRing, yfull0 = xempty0 + 8 * kWgXRing;
   const uint32_t yempty0 = yfull0 + 8 * kWgYRing, tfull = yempty0 + 8 * kWgYRing, tempty = tfull + 8, tmem_slot = tempty + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.map_x0);
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_strip_kernel(const __grid_consta
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   const long long lo0 = p.rows_total * blockIdx.x / gridDim.x;
   const long long hi0 = p.rows_total * (blockIdx.x + 1) / gridDim.x;
@@ -298,10 +300,10 @@ int wgrad_strip_launch(const xv2_tc_conv* q, const void* src0, const void* src1,
   cudaError_t e;
   if (krowb == 128) {
     e = cudaFuncSetAttribute(wgrad_strip_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) wgrad_strip_kernel<128><<<(unsigned)grid, 192, smem, as_stream(stream)>>>(p);
+    if (e == cudaSuccess) e = launch_pdl(wgrad_strip_kernel<128>, dim3((unsigned)grid), dim3(192), smem, as_stream(stream), p);
   } else {
     e = cudaFuncSetAttribute(wgrad_strip_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) wgrad_strip_kernel<64><<<(unsigned)grid, 192, smem, as_stream(stream)>>>(p);
+    if (e == cudaSuccess) e = launch_pdl(wgrad_strip_kernel<64>, dim3((unsigned)grid), dim3(192), smem, as_stream(stream), p);
   }
   if (e != cudaSuccess) {
     set_error("wgrad_strip: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
