@@ -297,6 +297,22 @@ int xv2_save_probs(const float* logits, int32_t n, int64_t hw, int32_t ncls, flo
  * [n][hw][2c]; scale / shift / mean / invstd fp32 [2c] as written by xv2_bn_finalize; the post-BN activation is never stored.
  * XV2_EUNSUPPORTED unless c / 8 is a power of two <= 128 (the caller then runs the unfused chain).
  * ---------------------------------------------------------------------------------------------------------- */
+/* xv2_splat_bn_gap with the bn0 finalize step folded in (one launch fewer per bottleneck): the coefficients come straight from
+ * the fp64 (sum, sum of squares) `stats` of the radix conv's epilogue; block (0,0) writes coef = [4][2c] mean | invstd | scale |
+ * shift for the later kernels and updates the running statistics exactly as xv2_bn_finalize does.  gap_is_zero != 0: the caller
+ * hands in zero-filled memory (the step's scratch arena) and no memset node is issued. */
+int xv2_splat_bn_gap_fin(const void* z, const double* stats, int64_t count, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float momentum, float eps, float* coef, float* gap,
+                         int32_t gap_is_zero, int32_t n, int64_t hw, int32_t c, void* stream);
+/* xv2_splat_fc_bwd for the bn0-fused path with the two tiny neighbours folded in (two launches fewer per bottleneck): datt is
+ * derived from `part` (as xv2_splat_bn_bwd_datt) inside the first FC kernel, and the bn0 reductions `red` (as
+ * xv2_splat_bn_bwd_red) are finished by the last one, which has just produced dgap.  accumulate != 0: dw2 / db2 / dw1 / db1 /
+ * dgamma / dbeta are ADDED TO (the parameters' own slots of the flat gradient buffer: no autograd accumulation launches). */
+int xv2_splat_fc_bwd_fused(const float* att, const double* part, const float* scale0, const float* shift0, const float* mean0,
+                           const float* invstd0, int64_t hw, const float* a1, const float* z1, const float* coef,
+                           const float* gamma, const float* gap, const float* w2t, const float* w1t, int32_t training,
+                           float* dz2, float* dz1, float* dw2, float* db2, float* dw1, float* db1, float* dgamma, float* dbeta,
+                           float* dgap, double* red, int32_t accumulate, int32_t n, int32_t c, int32_t inter, void* stream);
 /* gap[n][c] = mean_hw (relu(bn(z_0)) + relu(bn(z_1)))  (gap is zero-filled here) */
 int xv2_splat_bn_gap(const void* z, const float* scale, const float* shift, float* gap, int32_t n, int64_t hw, int32_t c,
                      void* stream);

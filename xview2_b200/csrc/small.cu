@@ -446,10 +446,21 @@ __global__ void __launch_bounds__(256) sa_fc2_rsoftmax_kernel(const float* __res
 }
 
 // backward 1: warp per radix pair k: dz2[:, k], dz2[:, k + C]; dw2 rows; db2
+// Optional inputs of the bn0-fused split attention (splat_fused.cu): with `part` (fp64 [4][n][2c] per-image partial sums A1 | A2 |
+// M1 | M2) the first FC kernel derives datt = scale0 * A2 + shift0 * A1 itself and the last one finishes the two bn0 reductions
+// (red fp64 [2][2c]) from the dgap column it has just produced -- the arithmetic of splat_bn_bwd_datt_kernel / splat_bn_bwd_red_kernel.
+struct SaFused {
+  const double* part;
+  const float *scale0, *shift0, *mean0, *invstd0;
+  double* red;
+  float inv_hw;
+  int accumulate;  // parameter gradients are ADDED to their destinations (the parameters' own slots in the flat gradient buffer)
+};
+
 __global__ void __launch_bounds__(256) sa_bwd_fc2_kernel(const float* __restrict__ att, const float* __restrict__ datt,
                                                          const float* __restrict__ a1, float* __restrict__ dz2,
                                                          float* __restrict__ dw2, float* __restrict__ db2, int n, int c,
-                                                         int inter) {
+                                                         int inter, SaFused fz) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -459,7 +470,16 @@ __global__ void __launch_bounds__(256) sa_bwd_fc2_kernel(const float* __restrict
   float s0 = 0.f, s1 = 0.f;
   for (int i = 0; i < n; ++i) {
     const long long i0 = (long long)i * 2 * c + k, i1 = i0 + c;
-    const float p0 = att[i0], p1 = att[i1], g0 = datt[i0], g1 = datt[i1];
+    const float p0 = att[i0], p1 = att[i1];
+    float g0, g1;
+    if (fz.part != nullptr) {
+      const long long plane = (long long)n * 2 * c;
+      g0 = (float)((double)fz.scale0[k] * fz.part[plane + i0] + (double)fz.shift0[k] * fz.part[i0]);
+      g1 = (float)((double)fz.scale0[k + c] * fz.part[plane + i1] + (double)fz.shift0[k + c] * fz.part[i1]);
+    } else {
+      g0 = datt[i0];
+      g1 = datt[i1];
+    }
     const float dot = p0 * g0 + p1 * g1;
     d0[i] = p0 * (g0 - dot);
     d1[i] = p1 * (g1 - dot);
@@ -467,8 +487,8 @@ __global__ void __launch_bounds__(256) sa_bwd_fc2_kernel(const float* __restrict
     s1 += d1[i];
   }
   if (lane == 0) {
-    db2[k] = s0;
-    db2[k + c] = s1;
+    db2[k] = (fz.accumulate ? db2[k] : 0.f) + s0;
+    db2[k + c] = (fz.accumulate ? db2[k + c] : 0.f) + s1;
   }
   for (int i = lane; i < n; i += 32) {
     dz2[(long long)i * 2 * c + k] = d0[i];
@@ -481,8 +501,8 @@ __global__ void __launch_bounds__(256) sa_bwd_fc2_kernel(const float* __restrict
       w0 = fmaf(d0[i], a, w0);
       w1 = fmaf(d1[i], a, w1);
     }
-    dw2[(long long)k * inter + j] = w0;
-    dw2[(long long)(k + c) * inter + j] = w1;
+    dw2[(long long)k * inter + j] = (fz.accumulate ? dw2[(long long)k * inter + j] : 0.f) + w0;
+    dw2[(long long)(k + c) * inter + j] = (fz.accumulate ? dw2[(long long)(k + c) * inter + j] : 0.f) + w1;
   }
 }
 
@@ -492,7 +512,7 @@ __global__ void __launch_bounds__(256) sa_bwd_bn_fc1_kernel(const float* __restr
                                                             const float* __restrict__ gamma, const float* __restrict__ gap,
                                                             int training, float* __restrict__ dz1, float* __restrict__ dw1,
                                                             float* __restrict__ db1, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int n, int c, int inter) {
+                                                            float* __restrict__ dbeta, int n, int c, int inter, int accumulate) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -520,21 +540,22 @@ __global__ void __launch_bounds__(256) sa_bwd_bn_fc1_kernel(const float* __restr
     bsum += d[i];
   }
   if (lane == 0) {
-    dbeta[j] = r1;
-    dgamma[j] = r2;
-    db1[j] = bsum;
+    dbeta[j] = (accumulate ? dbeta[j] : 0.f) + r1;
+    dgamma[j] = (accumulate ? dgamma[j] : 0.f) + r2;
+    db1[j] = (accumulate ? db1[j] : 0.f) + bsum;
   }
   for (int i = lane; i < n; i += 32) dz1[(long long)i * inter + j] = d[i];
   for (int cc = lane; cc < c; cc += 32) {
     float w = 0.f;
     for (int i = 0; i < n; ++i) w = fmaf(d[i], gap[(long long)i * c + cc], w);
-    dw1[(long long)j * c + cc] = w;
+    dw1[(long long)j * c + cc] = (accumulate ? dw1[(long long)j * c + cc] : 0.f) + w;
   }
 }
 
 // backward 3: dgap[n][c] = sum_j dz1[n][j] w1t[c][j]  (w1t = fc1's weight transposed: [c][inter]); warp per channel c
 __global__ void __launch_bounds__(256) sa_bwd_gap_kernel(const float* __restrict__ dz1, const float* __restrict__ w1t,
-                                                         float* __restrict__ dgap, int n, int c, int inter) {
+                                                         float* __restrict__ dgap, int n, int c, int inter,
+                                                         const float* __restrict__ att, SaFused fz) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -543,6 +564,22 @@ __global__ void __launch_bounds__(256) sa_bwd_gap_kernel(const float* __restrict
   float o[kSaMaxN];
   warp_matvec(dz1, w1t + (long long)cc * inter, n, inter, lane, o);
   for (int i = lane; i < n; i += 32) dgap[(long long)i * c + cc] = o[i];
+  if (fz.red != nullptr && lane < 2) {
+    // bn0 reductions of the radix halves ch = cc (lane 0) and cc + c (lane 1): both share this dgap column
+    const int c2 = 2 * c, ch = cc + lane * c;
+    const long long plane = (long long)n * c2;
+    const double mu = fz.mean0[ch], is = fz.invstd0[ch];
+    double r1 = 0.0, r2 = 0.0;
+    for (int nb = 0; nb < n; ++nb) {
+      const long long i = (long long)nb * c2 + ch;
+      const double a = att[i], g = (double)o[nb] * fz.inv_hw;
+      const double A1 = fz.part[i], A2 = fz.part[plane + i], M1 = fz.part[2 * plane + i], M2 = fz.part[3 * plane + i];
+      r1 += a * A1 + g * M1;
+      r2 += is * (a * (A2 - mu * A1) + g * (M2 - mu * M1));
+    }
+    fz.red[ch] = r1;
+    fz.red[c2 + ch] = r2;
+  }
 }
 }  // namespace xv2
 
@@ -570,10 +607,40 @@ extern "C" int xv2_splat_fc_bwd(const float* att, const float* datt, const float
                   dgap,
               "splat_fc_bwd: null argument");
   XV2_REQUIRE(n >= 1 && n <= kSaMaxN && c % 4 == 0 && inter % 4 == 0, "splat_fc_bwd: n <= 32, channels multiples of 4");
-  launch_pdl(sa_bwd_fc2_kernel, dim3((c + 7) / 8), dim3(256), 0, as_stream(stream), att, datt, a1, dz2, dw2, db2, n, c, inter);
+  SaFused fz;
+  memset(&fz, 0, sizeof(fz));
+  launch_pdl(sa_bwd_fc2_kernel, dim3((c + 7) / 8), dim3(256), 0, as_stream(stream), att, datt, a1, dz2, dw2, db2, n, c, inter, fz);
   launch_pdl(sa_bwd_bn_fc1_kernel, dim3((inter + 7) / 8), dim3(256), 0, as_stream(stream), dz2, w2t, z1, coef, gamma, gap, training, dz1, dw1, db1, dgamma,
-                                                                       dbeta, n, c, inter);
-  launch_pdl(sa_bwd_gap_kernel, dim3((c + 7) / 8), dim3(256), 0, as_stream(stream), dz1, w1t, dgap, n, c, inter);
+                                                                       dbeta, n, c, inter, 0);
+  launch_pdl(sa_bwd_gap_kernel, dim3((c + 7) / 8), dim3(256), 0, as_stream(stream), dz1, w1t, dgap, n, c, inter, att, fz);
+  XV2_LAUNCH_CHECK();
+  return XV2_OK;
+}
+
+extern "C" int xv2_splat_fc_bwd_fused(const float* att, const double* part, const float* scale0, const float* shift0,
+                                      const float* mean0, const float* invstd0, int64_t hw, const float* a1, const float* z1,
+                                      const float* coef, const float* gamma, const float* gap, const float* w2t, const float* w1t,
+                                      int32_t training, float* dz2, float* dz1, float* dw2, float* db2, float* dw1, float* db1,
+                                      float* dgamma, float* dbeta, float* dgap, double* red, int32_t accumulate, int32_t n, int32_t c,
+                                      int32_t inter, void* stream) {
+  XV2_REQUIRE(att && part && scale0 && shift0 && mean0 && invstd0 && a1 && z1 && coef && gap && w2t && w1t && dz2 && dz1 && dw2 &&
+                  db2 && dw1 && db1 && dgamma && dbeta && dgap && red && hw > 0,
+              "splat_fc_bwd_fused: null argument");
+  XV2_REQUIRE(n >= 1 && n <= kSaMaxN && c % 4 == 0 && inter % 4 == 0, "splat_fc_bwd_fused: n <= 32, channels multiples of 4");
+  SaFused fz;
+  fz.part = part;
+  fz.scale0 = scale0;
+  fz.shift0 = shift0;
+  fz.mean0 = mean0;
+  fz.invstd0 = invstd0;
+  fz.red = red;
+  fz.inv_hw = 1.0f / (float)hw;
+  fz.accumulate = accumulate ? 1 : 0;
+  launch_pdl(sa_bwd_fc2_kernel, dim3((c + 7) / 8), dim3(256), 0, as_stream(stream), att, (const float*)nullptr, a1, dz2, dw2, db2, n,
+             c, inter, fz);
+  launch_pdl(sa_bwd_bn_fc1_kernel, dim3((inter + 7) / 8), dim3(256), 0, as_stream(stream), dz2, w2t, z1, coef, gamma, gap, training,
+             dz1, dw1, db1, dgamma, dbeta, n, c, inter, accumulate);
+  launch_pdl(sa_bwd_gap_kernel, dim3((c + 7) / 8), dim3(256), 0, as_stream(stream), dz1, w1t, dgap, n, c, inter, att, fz);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }

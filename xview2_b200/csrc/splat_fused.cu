@@ -85,17 +85,65 @@ __device__ __forceinline__ void block_reduce_vec8(float (*sm)[8], float* vals, i
 }
 
 // ---- forward 1: gap ------------------------------------------------------------------------------------------
+// nn.BatchNorm2d training statistics of one channel from the fp64 (sum, sum of squares): the arithmetic of bn_finalize_kernel (bn.cu)
+struct SplatFin {
+  const double* stats;        // fp64 [2 * 2c]; null: scale / shift are read from memory
+  const float *gamma, *beta;
+  float *rmean, *rvar;        // running statistics (may be null), updated by block (0, 0)
+  float* coef;                // [4][2c] mean | invstd | scale | shift, written by block (0, 0)
+  float momentum, eps;
+  long long count;
+};
+__device__ __forceinline__ void splat_finalize_channel(const SplatFin& f, int c2, int ch, float* mean, float* invstd, float* scale,
+                                                       float* shift, double* var_out) {
+  const double n = (double)f.count;
+  const double mu = f.stats[ch] / n;
+  double var = f.stats[c2 + ch] / n - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)f.eps));
+  const float g = f.gamma ? f.gamma[ch] : 1.f, b = f.beta ? f.beta[ch] : 0.f;
+  *mean = (float)mu;
+  *invstd = is;
+  *scale = g * is;
+  *shift = b - (float)mu * g * is;
+  *var_out = var;
+}
+
 __global__ void __launch_bounds__(256) splat_bn_gap_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, float* __restrict__ gap,
-                                                           long long hw, int c, float inv_hw, SplatMap m) {
+                                                           long long hw, int c, float inv_hw, SplatMap m, SplatFin fin) {
   __shared__ float sm[256][8];
   const int cvi = threadIdx.x % m.cvt, lane = threadIdx.x / m.cvt;
   const int ch0 = cvi * 8, nb = blockIdx.y;
+  if (fin.stats != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+    // fused finalize: this block publishes the coefficients the later kernels read and updates the running statistics
+    for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) {
+      float mean, invstd, scl, sft;
+      double var;
+      splat_finalize_channel(fin, 2 * c, i, &mean, &invstd, &scl, &sft, &var);
+      fin.coef[i] = mean;
+      fin.coef[2 * c + i] = invstd;
+      fin.coef[4 * c + i] = scl;
+      fin.coef[6 * c + i] = sft;
+      if (fin.rmean) {
+        const double n = (double)fin.count;
+        const double unbiased = fin.count > 1 ? var * n / (n - 1.0) : var;
+        fin.rmean[i] = (1.f - fin.momentum) * fin.rmean[i] + fin.momentum * mean;
+        fin.rvar[i] = (1.f - fin.momentum) * fin.rvar[i] + fin.momentum * (float)unbiased;
+      }
+    }
+  }
   float sc[8], sh[8], acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    sc[i] = scale[ch0 + i];
-    sh[i] = shift[ch0 + i];
+    if (fin.stats != nullptr) {
+      float mean, invstd;
+      double var;
+      splat_finalize_channel(fin, 2 * c, ch0 + i, &mean, &invstd, &sc[i], &sh[i], &var);
+    } else {
+      sc[i] = scale[ch0 + i];
+      sh[i] = shift[ch0 + i];
+    }
     acc[i] = 0.f;
   }
   const __nv_bfloat16* zb = z + (long long)nb * hw * 2 * c + ch0;
@@ -355,8 +403,33 @@ extern "C" int xv2_splat_bn_gap(const void* z, const float* scale, const float* 
   XV2_SPLAT_SHAPE("splat_bn_gap", 2 * c / 8)
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(gap, 0, sizeof(float) * (size_t)n * c, st);
+  SplatFin fin;
+  memset(&fin, 0, sizeof(fin));
   splat_bn_gap_kernel<<<splat_grid(n, hw, m.lanes, 16), 256, 0, st>>>((const __nv_bfloat16*)z, scale, shift, gap, hw, c,
-                                                                     1.0f / (float)hw, m);
+                                                                     1.0f / (float)hw, m, fin);
+  XV2_LAUNCH_CHECK();
+  return XV2_OK;
+}
+
+extern "C" int xv2_splat_bn_gap_fin(const void* z, const double* stats, int64_t count, const float* gamma, const float* beta,
+                                    float* running_mean, float* running_var, float momentum, float eps, float* coef, float* gap,
+                                    int32_t gap_is_zero, int32_t n, int64_t hw, int32_t c, void* stream) {
+  XV2_REQUIRE(z && stats && coef && gap && count > 0, "splat_bn_gap_fin: bad argument");
+  XV2_SPLAT_SHAPE("splat_bn_gap_fin", 2 * c / 8)
+  cudaStream_t st = as_stream(stream);
+  if (!gap_is_zero) cudaMemsetAsync(gap, 0, sizeof(float) * (size_t)n * c, st);
+  SplatFin fin;
+  fin.stats = stats;
+  fin.gamma = gamma;
+  fin.beta = beta;
+  fin.rmean = running_mean;
+  fin.rvar = running_var;
+  fin.coef = coef;
+  fin.momentum = momentum;
+  fin.eps = eps;
+  fin.count = count;
+  splat_bn_gap_kernel<<<splat_grid(n, hw, m.lanes, 16), 256, 0, st>>>((const __nv_bfloat16*)z, nullptr, nullptr, gap, hw, c,
+                                                                     1.0f / (float)hw, m, fin);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }

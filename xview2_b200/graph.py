@@ -69,8 +69,10 @@ class GraphedTrainStep:
         self.optimizer.step_captured()
 
     def _forward_backward(self):
+        from . import ops
         self.optimizer.zero_grad()
-        loss = self.model.training_step(self.static, 0)
+        with ops.defer_nbt():  # the 81 num_batches_tracked += 1 launches of the forward become one multi-tensor add
+            loss = self.model.training_step(self.static, 0)
         loss.backward()
         return loss.detach()
 

@@ -265,6 +265,7 @@ class _Conv2d(torch.autograd.Function):
         if stats is None:
             stats = torch.empty(0, dtype=torch.float64, device=out.device)
         ctx.mark_non_differentiable(stats)
+        ctx.set_materialize_grads(False)  # else autograd launches a zero-fill for the statistics' "gradient" before every backward
         return out, stats
 
     @staticmethod
@@ -313,6 +314,8 @@ class _Conv2d(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dstats=None):
+        if dy is None:
+            return (None,) * 9
         x, x2, weight = ctx.saved_tensors
         stride, pad, dil, groups, c0, c1 = ctx.cfg
         dy = nhwc(dy)
@@ -603,10 +606,52 @@ def fork(x):
     return x, x
 
 
+# nn.BatchNorm2d.num_batches_tracked += 1 is one tiny launch per BatchNorm per step (81 at config 2).  Inside `defer_nbt()` (the
+# captured training step) the bumps are collected and applied by one multi-tensor add per multiplicity at the end of the forward.
+_nbt_pending = None
+
+
+class defer_nbt:
+    def __enter__(self):
+        global _nbt_pending
+        self.prev, _nbt_pending = _nbt_pending, []
+        return self
+
+    def __exit__(self, *exc):
+        global _nbt_pending
+        pending, _nbt_pending = _nbt_pending, self.prev
+        if exc[0] is None and pending:
+            count = {}
+            for t in pending:
+                count.setdefault(id(t), [t, 0])[1] += 1
+            for m in sorted({c for _, c in count.values()}):
+                torch._foreach_add_([t for t, c in count.values() if c == m], m)
+        return False
+
+
+def _bump_nbt(bn):
+    t = bn.num_batches_tracked
+    if t is None:
+        return
+    if _nbt_pending is not None:
+        _nbt_pending.append(t)
+    else:
+        t += 1
+
+
+def _flat_grads(*params):
+    """The parameters' own gradient slots in the flat buffer (optim.FlatParams; zeroed once per step) when ALL of them have one:
+    kernels add into them directly and autograd launches no accumulation kernel."""
+    if all(p is not None and getattr(p, "_xv2_flat", False) and p.grad is not None and p.grad.dtype == torch.float32 and
+           p.grad.is_contiguous() for p in params):
+        return tuple(p.grad for p in params)
+    return None
+
+
 def batch_norm_act(x, bn, act=ACT_NONE, residual=None, stats=None):
     """Applies the nn.BatchNorm2d module `bn` (its parameters / buffers / training flag) followed by `act`."""
-    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+    if bn.training and bn.track_running_stats:
+        _bump_nbt(bn)
     use_batch = bn.training or not bn.track_running_stats
     y = _BatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch,
                             bn.momentum if bn.momentum is not None else 0.1, bn.eps, act, stats if use_batch else None)
@@ -699,6 +744,7 @@ class _BNActHead(torch.autograd.Function):
         ctx.save_for_backward(z, gamma, coef, w2)
         ctx.cfg = (act, head_w.shape, head_b is not None)
         ctx.flat_grads = _flat_grad_pair(gamma, beta)
+        ctx.head_flat = _flat_grads(head_w, head_b) if head_b is not None else None
         return logits
 
     @staticmethod
@@ -711,8 +757,9 @@ class _BNActHead(torch.autograd.Function):
         dev = z.device
         dl = nhwc(dl.float())
         red = zeros_scratch(2 * c, torch.float64, dev)
-        dhw = zeros_scratch((ncls, c), torch.float32, dev)
-        dhb = zeros_scratch(ncls, torch.float32, dev)
+        hflat = ctx.head_flat  # head weight / bias slots of the flat gradient buffer: the reduce kernel atomically adds into them
+        dhw = hflat[0] if hflat is not None else zeros_scratch((ncls, c), torch.float32, dev)
+        dhb = hflat[1] if hflat is not None else zeros_scratch(ncls, torch.float32, dev)
         lib.note_work(0.0, 2.0 * pixels * c + 4.0 * pixels * ncls, f"bn+act+head bwd reduce n{n} {h}x{w} c{c}")
         call("xv2_bnact_head_bwd_reduce", ptr(z), ptr(dl), pixels, c, ptr(coef[2]), ptr(coef[3]), ptr(coef[0]), ptr(coef[1]), act,
              ptr(w2), ncls, ptr(red), ptr(dhw), ptr(dhb))
@@ -723,6 +770,9 @@ class _BNActHead(torch.autograd.Function):
         call("xv2_bnact_head_bwd_apply", ptr(z), ptr(dl), ptr(dz), pixels, c, ptr(coef[2]), ptr(coef[3]), ptr(coef[0]), ptr(coef[1]),
              ptr(gamma), act, ptr(w2), ncls, ptr(red), pixels, ptr(gg if gg is not None else dgb[0]),
              ptr(gb if gb is not None else dgb[1]), 1 if gg is not None else 0)
+        if hflat is not None:
+            return (dz, None, None if gg is not None else dgb[0], None if gg is not None else dgb[1], None, None, None, None, None,
+                    None, None)
         return (dz, None, None if gg is not None else dgb[0], None if gg is not None else dgb[1], None, None, None, None, None,
                 dhw.clone().reshape(wshape), dhb.clone() if has_bias else None)
 
@@ -754,8 +804,7 @@ def bnact_head(deferred, head_w, head_b):
     if stats is None:
         stats = zeros_scratch(2 * c, torch.float64, z.device)
         call("xv2_bn_stats", ptr(z), n * h * w, c, dtype_code(z), ptr(stats))
-    if bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+    _bump_nbt(bn)
     return _BNActHead.apply(z, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                             bn.momentum if bn.momentum is not None else 0.1, bn.eps, deferred.act, head_w, head_b)
 
@@ -992,11 +1041,11 @@ class _BnSplitAttention(torch.autograd.Function):
         inter = w1.shape[0]
         dev = z.device
         coef0 = torch.empty(4, c2, dtype=torch.float32, device=dev)  # mean, invstd, scale, shift of bn0
-        call("xv2_bn_finalize", ptr(stats), n * hw, c2, ptr(g0), ptr(b0), ptr(rm0), ptr(rv0), float(mom0), float(eps0),
-             ptr(coef0[0]), ptr(coef0[1]), ptr(coef0[2]), ptr(coef0[3]))
-        gap = torch.empty((n, c), dtype=torch.float32, device=dev)
+        gap = zeros_scratch((n, c), torch.float32, dev)  # zero-filled with the step's arena: no memset node of its own
         lib.note_work(0.0, 2.0 * n * hw * c2, f"splat bn+gap n{n} {h}x{w} c{c}")
-        call("xv2_splat_bn_gap", ptr(z), ptr(coef0[2]), ptr(coef0[3]), ptr(gap), n, hw, c)
+        # bn0's finalize step (coefficients, running statistics) is folded into the GAP kernel's prologue
+        call("xv2_splat_bn_gap_fin", ptr(z), ptr(stats), n * hw, ptr(g0), ptr(b0), ptr(rm0), ptr(rv0), float(mom0), float(eps0),
+             ptr(coef0), ptr(gap), 1, n, hw, c)
         w1m, w2m = w1.reshape(inter, c).contiguous(), w2.reshape(c2, inter).contiguous()
         z1 = torch.empty((n, inter), dtype=torch.float32, device=dev)
         a1 = torch.empty_like(z1)
@@ -1010,6 +1059,7 @@ class _BnSplitAttention(torch.autograd.Function):
         ctx.save_for_backward(z, att, gap, z1, a1, coef, coef0, w1, w2, gamma, g0)
         ctx.training = training
         ctx.flat_grads = _flat_grad_pair(g0, b0)
+        ctx.fc_flat = _flat_grads(w1, b1, gamma, beta, w2, b2)
         return out
 
     @staticmethod
@@ -1025,21 +1075,24 @@ class _BnSplitAttention(torch.autograd.Function):
         part = zeros_scratch((4, n, c2), torch.float64, dev)
         lib.note_work(0.0, 2.0 * n * hw * (c2 + c), f"splat bn bwd partials n{n} {h}x{w} c{c}")
         call("xv2_splat_bn_bwd_partials", ptr(z), ptr(dout), ptr(coef0[2]), ptr(coef0[3]), ptr(part), n, hw, c)
-        datt = torch.empty((n, c2), dtype=torch.float32, device=dev)
-        call("xv2_splat_bn_bwd_datt", ptr(part), ptr(coef0[2]), ptr(coef0[3]), ptr(datt), n, c)
         w2t = pack_weight(w2, 1, torch.float32)  # [inter][2c]
         w1t = pack_weight(w1, 1, torch.float32)  # [c][inter]
         scratch = torch.empty(n * (c2 + inter), dtype=torch.float32, device=dev)
-        dw2 = torch.empty((c2, inter), dtype=torch.float32, device=dev)
-        dw1 = torch.empty((inter, c), dtype=torch.float32, device=dev)
-        small = torch.empty(c2 + 3 * inter, dtype=torch.float32, device=dev)
-        db2, db1, dgamma, dbeta = small[:c2], small[c2:c2 + inter], small[c2 + inter:c2 + 2 * inter], small[c2 + 2 * inter:]
+        fcf = ctx.fc_flat
+        if fcf is not None:  # the FC parameters' own slots in the flat gradient buffer: the kernels add to them
+            dw1, db1, dgamma, dbeta, dw2, db2 = fcf
+        else:
+            dw2 = torch.empty((c2, inter), dtype=torch.float32, device=dev)
+            dw1 = torch.empty((inter, c), dtype=torch.float32, device=dev)
+            small = torch.empty(c2 + 3 * inter, dtype=torch.float32, device=dev)
+            db2, db1, dgamma, dbeta = small[:c2], small[c2:c2 + inter], small[c2 + inter:c2 + 2 * inter], small[c2 + 2 * inter:]
         dgap = torch.empty((n, c), dtype=torch.float32, device=dev)
-        call("xv2_splat_fc_bwd", ptr(att), ptr(datt), ptr(a1), ptr(z1), ptr(coef), ptr(gamma), ptr(gap), ptr(w2t), ptr(w1t),
-             int(bool(training)), ptr(scratch), ptr(scratch[n * c2:]), ptr(dw2), ptr(db2), ptr(dw1), ptr(db1), ptr(dgamma),
-             ptr(dbeta), ptr(dgap), n, c, inter)
         red = torch.empty(2 * c2, dtype=torch.float64, device=dev)
-        call("xv2_splat_bn_bwd_red", ptr(part), ptr(att), ptr(dgap), ptr(coef0[0]), ptr(coef0[1]), ptr(red), n, hw, c)
+        # datt (from the partial sums) and the two bn0 reductions are computed inside the FC-chain kernels
+        call("xv2_splat_fc_bwd_fused", ptr(att), ptr(part), ptr(coef0[2]), ptr(coef0[3]), ptr(coef0[0]), ptr(coef0[1]), hw,
+             ptr(a1), ptr(z1), ptr(coef), ptr(gamma), ptr(gap), ptr(w2t), ptr(w1t), int(bool(training)), ptr(scratch),
+             ptr(scratch[n * c2:]), ptr(dw2), ptr(db2), ptr(dw1), ptr(db1), ptr(dgamma), ptr(dbeta), ptr(dgap), ptr(red),
+             1 if fcf is not None else 0, n, c, inter)
         dz = torch.empty_like(z)
         gg, gb = ctx.flat_grads
         dgb0 = None if gg is not None else torch.empty(2, c2, dtype=torch.float32, device=dev)
@@ -1047,7 +1100,10 @@ class _BnSplitAttention(torch.autograd.Function):
         call("xv2_splat_bn_bwd_apply", ptr(z), ptr(dout), ptr(att), ptr(dgap), ptr(coef0[2]), ptr(coef0[3]), ptr(coef0[0]),
              ptr(coef0[1]), ptr(g0), ptr(red), ptr(dz), ptr(gg if gg is not None else dgb0[0]),
              ptr(gb if gb is not None else dgb0[1]), 1 if gg is not None else 0, n, hw, c)
-        return (dz, None, None if gg is not None else dgb0[0], None if gg is not None else dgb0[1], None, None, None, None,
+        g0b0 = (None, None) if gg is not None else (dgb0[0], dgb0[1])
+        if fcf is not None:
+            return (dz, None, *g0b0, None, None, None, None, None, None, None, None, None, None, None, None, None, None, None)
+        return (dz, None, *g0b0, None, None, None, None,
                 dw1.reshape(w1.shape), db1, dgamma, dbeta, None, None, dw2.reshape(w2.shape), db2, None, None, None)
 
 
@@ -1067,8 +1123,7 @@ def conv_bn_split_attention(x, conv, bn0, fc1, bn1, fc2):
         stats = zeros_scratch(2 * c2, torch.float64, z.device)
         call("xv2_bn_stats", ptr(z), z.shape[0] * z.shape[2] * z.shape[3], c2, dtype_code(z), ptr(stats))
     for bn in (bn0, bn1):
-        if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
+        _bump_nbt(bn)
     return _BnSplitAttention.apply(z, stats, bn0.weight, bn0.bias, bn0.running_mean, bn0.running_var,
                                    bn0.momentum if bn0.momentum is not None else 0.1, bn0.eps, fc1.weight, fc1.bias,
                                    bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, fc2.weight, fc2.bias, True,
@@ -1077,8 +1132,8 @@ def conv_bn_split_attention(x, conv, bn0, fc1, bn1, fc2):
 
 def split_attention(x, fc1, bn1, fc2):
     """x: (n, 2c, h, w) after bn0+relu; fc1/fc2: nn.Conv2d 1x1 with bias; bn1: nn.BatchNorm2d on (n, inter, 1, 1)."""
-    if bn1.training and bn1.num_batches_tracked is not None:
-        bn1.num_batches_tracked += 1
+    if bn1.training:
+        _bump_nbt(bn1)
     return _SplitAttention.apply(x, fc1.weight, fc1.bias, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var,
                                  fc2.weight, fc2.bias, bn1.training, bn1.momentum, bn1.eps)
 
