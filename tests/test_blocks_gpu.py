@@ -221,7 +221,8 @@ def test_fused_bn_split_attention(channels, hw, n):
         mod_f, x_f, out = run(True)
     finally:
         ops.call = orig
-    assert "xv2_splat_bn_gap" in calls and "xv2_splat_bn_bwd_apply" in calls and "xv2_bn_train_apply" not in calls, calls
+    assert ("xv2_splat_bn_gap_fin" in calls and "xv2_splat_fc_bwd_fused" in calls and "xv2_splat_bn_bwd_apply" in calls and
+            "xv2_bn_train_apply" not in calls and "xv2_bn_finalize" not in calls), calls
     mod_u, x_u, out_u = run(False)  # the unfused chain on the same inputs: the yard-stick for what bf16 storage costs
 
     P = {"m." + k: v.detach().float().cpu().clone() for k, v in mod.state_dict().items()}
@@ -305,3 +306,59 @@ def test_fork_gradients_match_autograd_accumulation(kind, monkeypatch):
                 continue
             nk = l2(gp_b[k], gp_a[k])
             assert l2(gp_f[k], gp_a[k]) <= max(4 * nk, 5e-3), (k, l2(gp_f[k], gp_a[k]), nk)
+
+
+def test_flat_gradient_slots_receive_fc_and_head_gradients():
+    """With optim.FlatParams the split-attention FC chain and the fused BN + head kernels ADD their parameter gradients into
+    the parameters' own slots of the flat gradient buffer (no autograd accumulation launches): same values as the gradients
+    autograd returns without the flat buffer, and a second backward without zero_grad doubles them."""
+    import copy
+
+    from torch import nn
+
+    from xview2_b200 import ops
+    from xview2_b200.lib import ACT_LRELU
+    from xview2_b200.model.encoders import SplAtConv2d, _init_resnest
+    from xview2_b200.optim import FlatParams
+
+    class Tiny(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.sp = SplAtConv2d(64, 1)
+            self.bn = nn.BatchNorm2d(64)
+            self.head = nn.Conv2d(64, 2, 1)
+
+        def forward(self, x):
+            y = self.sp(x)
+            return ops.bnact_head(ops.DeferredBNAct(y, None, self.bn, ACT_LRELU), self.head.weight, self.head.bias)
+
+    torch.manual_seed(9)
+    net = Tiny()
+    _init_resnest(net.sp)
+    net = net.cuda().train()
+    g = torch.Generator().manual_seed(4)
+    x = ops.nhwc((torch.randn(4, 64, 32, 32, generator=g) * torch.tensor([0.5, 1.0, 2.0, 4.0]).view(4, 1, 1, 1)).cuda().to(torch.bfloat16))
+    gl = torch.randn(4, 2, 32, 32, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+
+    def grads(flat, passes=1):
+        m = copy.deepcopy(net)
+        fp = FlatParams(m) if flat else None
+        if fp is not None:
+            fp.zero_grad()
+        for _ in range(passes):
+            m(x).backward(gl)
+        ops.check_pending_addends()
+        torch.cuda.synchronize()
+        return {k: p.grad.detach().float().reshape(-1).clone() for k, p in m.named_parameters()}
+
+    def l2(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+    ga, gb = grads(False), grads(False)  # run-to-run noise of the plain path (fp32 atomics in GAP / weight gradients)
+    gf, gf2 = grads(True), grads(True, passes=2)
+    for k in ga:
+        if k.endswith("fc1.bias"):  # analytically zero (bias in front of a BatchNorm)
+            continue
+        tol = max(4 * l2(gb[k], ga[k]), 5e-3)
+        assert l2(gf[k], ga[k]) <= tol, (k, l2(gf[k], ga[k]), tol)
+        assert l2(gf2[k], 2 * ga[k]) <= 2 * tol, (k, l2(gf2[k], 2 * ga[k]), tol)
