@@ -535,3 +535,46 @@ def test_state_dict_keys_match_reference(name):
     assert not missing and not extra, (missing[:5], extra[:5])
     wrong = [(k, ours[k], ref[k]) for k in ref if ours[k] != ref[k]]
     assert not wrong, wrong[:5]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# gradient plumbing of the captured step (host logic only)
+# ---------------------------------------------------------------------------------------------------------------
+def test_fork_parks_second_gradient_part_and_unclaimed_parts_fail_loudly():
+    """ops.fork hands one gradient part on and parks the other for the producer's BatchNorm backward; if nobody collects it
+    the step-boundary check raises instead of training on a silently incomplete gradient."""
+    from xview2_b200 import ops
+
+    x = torch.randn(2, 8, 4, 4, requires_grad=True)
+    y = x * 1.0
+    assert ops.fork(y)[0] is y and ops.fork(y)[1] is y      # not a train-mode BatchNorm output: plain aliases, autograd accumulates
+    y._xv2_forkable = True
+    a, b = ops.fork(y)
+    assert a is not y and a.data_ptr() == y.data_ptr() and b.data_ptr() == y.data_ptr()
+    (a.sum() + 2.0 * b.sum()).backward()                     # the consumer here is a plain multiply: nobody pops the parked part
+    assert torch.equal(x.grad, torch.ones_like(x))           # only the first part travelled on
+    with pytest.raises(RuntimeError, match="never consumed"):
+        ops.check_pending_addends()
+    ops.check_pending_addends()                              # the table is cleared by the failure
+    with torch.no_grad():
+        assert ops.fork(y)[0] is y                           # no tape: no fork
+
+
+def test_deferred_num_batches_tracked_counts_every_visit():
+    """ops.defer_nbt: the per-BatchNorm `num_batches_tracked += 1` launches of a forward are applied as one multi-tensor add per
+    multiplicity (a module visited twice -- Siamese encoders -- is bumped by two)."""
+    from xview2_b200 import ops
+
+    bns = [torch.nn.BatchNorm2d(4) for _ in range(3)]
+    with ops.defer_nbt():
+        for bn in (bns[0], bns[1], bns[0], bns[2], bns[0]):
+            ops._bump_nbt(bn)
+        assert all(int(bn.num_batches_tracked) == 0 for bn in bns)   # nothing applied yet
+    assert [int(bn.num_batches_tracked) for bn in bns] == [3, 1, 1]
+    ops._bump_nbt(bns[1])                                              # outside the context: immediate
+    assert int(bns[1].num_batches_tracked) == 2
+    with pytest.raises(ValueError):
+        with ops.defer_nbt():
+            ops._bump_nbt(bns[2])
+            raise ValueError("forward failed")
+    assert int(bns[2].num_batches_tracked) == 1                        # a failed forward applies nothing

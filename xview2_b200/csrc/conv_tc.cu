@@ -1000,7 +1000,9 @@ extern "C" int xv2_wgrad_tc(const xv2_tc_conv* q, const void* src0, const void* 
   p.pix = pix;
   p.dw = dw;
   const long long units = (long long)p.m_tiles * p.n_tiles * groups;
-  long long splits = (2LL * g_num_sms + units - 1) / units;
+  // split the pixel axis so that the grid fills at most TWO whole waves of one CTA per SM: rounding the split count UP (304 or
+  // 320 CTAs for the layer3 / layer4 1x1 shapes, ncu row 80 of profiles/r02_ncu_kernels.md) left a third, nearly empty wave
+  long long splits = (2LL * g_num_sms) / units;
   if (splits > p.pix_tiles) splits = p.pix_tiles;
   if (splits < 1) splits = 1;
   // re-balance so that no split is empty

@@ -262,6 +262,27 @@ __global__ void __launch_bounds__(256) pool3s2_bwd_quad_kernel(PoolGeom g, const
   }
 }
 
+// 2x2 / stride 2 / pad 0 average pool backward on even images (the ResNeSt avg-down shortcut): every input pixel belongs to
+// exactly one window -- one dy load, four dx stores per thread (same value as the generic gather: round(dy * 1/divisor))
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) avgpool2s2_bwd_quad_kernel(PoolGeom g, const T* __restrict__ dy, T* __restrict__ dx) {
+  const int cv = g.c / VEC;
+  const int rowsz = g.ow * cv;
+  const int nb = blockIdx.y / g.oh, a = blockIdx.y - nb * g.oh;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowsz; i += gridDim.x * blockDim.x) {
+    const int b = i / cv, cvi = i - b * cv;
+    float d[VEC];
+    pldv<T, VEC>(dy + (((long long)nb * g.oh + a) * g.ow + b) * g.c + cvi * VEC, d);
+    const float inv = 1.0f / avg_divisor(g, a, b, 2, 2);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) d[j] = fmaf(d[j], inv, 0.f);
+#pragma unroll
+    for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+      for (int dc = 0; dc < 2; ++dc) pstv<T, VEC>(dx + (((long long)nb * g.h + 2 * a + dr) * g.w + 2 * b + dc) * g.c + cvi * VEC, d);
+  }
+}
+
 static int pool_blocks(long long total) {
   long long b = cdiv(total, 256);
   if (b > 16 * kNumSMs) b = 16 * kNumSMs;
@@ -344,6 +365,16 @@ extern "C" int xv2_avgpool_bwd(const void* dy, void* dx, int32_t n, int32_t h, i
   XV2_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0 && k > 0 && stride > 0, "avgpool: bad shape");
   PoolGeom g{n, h, w, c, oh, ow, k, stride, pad, count_include_pad};
   if (quad_ok(h, w, c, oh, ow, k, stride, pad, dtype)) return launch_quad<false>(g, nullptr, dy, dx, dtype, stream);
+  if (quad_ok(h, w, c, oh, ow, 3, stride, 1, dtype) && k == 2 && pad == 0 && (long long)n * oh <= 65535) {  // same gate, 2x2 / 2 / 0 window
+    const int vecw = dtype == XV2_BF16 ? 8 : 4;
+    const dim3 grid((unsigned)std::min<long long>(cdiv((long long)ow * (c / vecw), 256), 64), (unsigned)(n * oh));
+    if (dtype == XV2_BF16)
+      avgpool2s2_bwd_quad_kernel<__nv_bfloat16, 8><<<grid, 256, 0, as_stream(stream)>>>(g, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx);
+    else
+      avgpool2s2_bwd_quad_kernel<float, 4><<<grid, 256, 0, as_stream(stream)>>>(g, (const float*)dy, (float*)dx);
+    XV2_LAUNCH_CHECK();
+    return XV2_OK;
+  }
   XV2_POOL_LAUNCH(avgpool_bwd_kernel, n, h, w, g, (const T*)dy, (T*)dx);
   return XV2_OK;
 }
