@@ -628,7 +628,8 @@ def run_ours(a):
                              "pinned uint8 HWC tiles + masks -> side-stream H2D (double-buffered TileRing) -> Model.forward (TTA) -> argmax label map + F1 counters -> uint8 label maps D2H into pinned memory, read on the host every step"),
                     "results_read": len(host_results)},
             "gpu_launches": launches,
-            "conv_roofline_frac": round(c["gflop"] * value / 1e3 / peaks["tensor"], 4),
+            # whole-job algorithmic conv FLOP rate against N GPUs' sustained bf16 peak: a per-GPU fraction
+            "conv_roofline_frac": round(c["gflop"] * value / 1e3 / (peaks["tensor"] * world), 4),
             "roofline": roof, "cpu_baseline": cpu_baseline, "cpu_baseline_c1": cpu_c1, "library_baseline": library,
             "clocks": clocks, "kernels": kernels, "loss": last_loss,
         }

@@ -491,3 +491,29 @@ def test_cat_unet_matches_oracle():
     ref = OF.model_forward({k: v.clone() for k, v in state.items()}, x, True, ns)
     assert out.shape == ref.shape == (4, 4, 64, 64)
     assert rel(out, ref) < 1e-3
+
+
+def test_batched_repack_equals_single_pack():
+    """xv2_pack_weights_batched (one launch per step; 32 x 32 shared-memory transposes for the dgrad / transposed-conv orders)
+    writes exactly what xv2_pack_weight (element-wise reference kernel) writes, for every mode / dtype / group count the
+    networks use -- including shapes that do not tile (the element-wise fallback inside the batched kernel)."""
+    ops = _ops()
+    cases = [((128, 64, 3, 3), 0, torch.bfloat16, 1), ((128, 64, 3, 3), 1, torch.bfloat16, 1), ((256, 64, 3, 3), 1, torch.bfloat16, 2),
+             ((64, 256, 1, 1), 1, torch.bfloat16, 1), ((128, 32, 2, 2), 2, torch.bfloat16, 1), ((512, 64, 1, 1), 1, torch.float32, 1),
+             ((32, 3, 3, 3), 0, torch.bfloat16, 1), ((48, 40, 3, 3), 1, torch.bfloat16, 1), ((2, 32, 1, 1), 1, torch.bfloat16, 1)]
+    ops.clear_weight_cache()
+    weights, single = [], []
+    for i, (shape, mode, dtype, groups) in enumerate(cases):
+        w = rnd(*shape, seed=20 + i).contiguous(memory_format=CL)
+        weights.append(w)
+        single.append(ops.pack_weight(w, mode, dtype, groups).clone())  # element-wise kernel
+    for w in weights:
+        w.mul_(1.0)  # bump the version: the cached copies are stale now
+    for (shape, mode, dtype, groups), w in zip(cases, weights):
+        ops.pack_weight(w, mode, dtype, groups).zero_()  # re-packs lazily (element-wise), then wiped so the batched launch must write
+    ops.clear_weight_cache()
+    ops.repack_all()
+    torch.cuda.synchronize()
+    for (shape, mode, dtype, groups), w, ref in zip(cases, weights, single):
+        got = ops.pack_weight(w, mode, dtype, groups)  # valid stamp: returned as the batched launch left it
+        assert torch.equal(got, ref), (shape, mode, dtype, groups)
