@@ -494,9 +494,8 @@ def test_cat_unet_matches_oracle():
 
 
 def test_batched_repack_equals_single_pack():
-    """xv2_pack_weights_batched (one launch per step; 32 x 32 shared-memory transposes for the dgrad / transposed-conv orders)
-    writes exactly what xv2_pack_weight (element-wise reference kernel) writes, for every mode / dtype / group count the
-    networks use -- including shapes that do not tile (the element-wise fallback inside the batched kernel)."""
+    """xv2_pack_weights_batched (one launch per step for every packed copy of the model) writes exactly what xv2_pack_weight
+    (one launch per weight) writes, for every mode / dtype / group count the networks use."""
     ops = _ops()
     cases = [((128, 64, 3, 3), 0, torch.bfloat16, 1), ((128, 64, 3, 3), 1, torch.bfloat16, 1), ((256, 64, 3, 3), 1, torch.bfloat16, 2),
              ((64, 256, 1, 1), 1, torch.bfloat16, 1), ((128, 32, 2, 2), 2, torch.bfloat16, 1), ((512, 64, 1, 1), 1, torch.float32, 1),

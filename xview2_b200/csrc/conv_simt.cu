@@ -265,41 +265,6 @@ __device__ __forceinline__ void pack_job(const xv2_pack_job& j) {
   const int a = j.a, r = j.r, s = j.s, b = j.b, mode = j.mode;
   const long long total = (long long)a * r * s * b;
   const int ag = a / j.groups;
-  if (mode != 0 && ag % 32 == 0 && b % 32 == 0) {
-    // Modes 1 / 2 transpose the (out-channel, in-channel) pair of every tap: per (group, tap) a [ag][b] -> [b][ag] transpose.
-    // 32 x 32 tiles through shared memory: 128-byte row reads and 32-element row writes (the element-wise loop below reads with
-    // a stride of r*s*b floats: one 32-byte sector per 4-byte element).
-    __shared__ float tile[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 256 threads: 8 rows per pass
-    const int ta = ag / 32, tb = b / 32;
-    const long long ntiles = (long long)j.groups * r * s * ta * tb;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      long long q = t;
-      const int bt = (int)(q % tb); q /= tb;
-      const int at = (int)(q % ta); q /= ta;
-      const int ss = (int)(q % s); q /= s;
-      const int rr = (int)(q % r);
-      const int grp = (int)(q / r);
-      const int ai0 = at * 32, bi0 = bt * 32;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int ai = ai0 + ty + 8 * k;
-        const long long si = mode == 2 ? (((long long)ai * r + rr) * s + ss) * b + bi0 + tx
-                                       : (((long long)(grp * ag + ai) * r + (r - 1 - rr)) * s + (s - 1 - ss)) * b + bi0 + tx;
-        tile[ty + 8 * k][tx] = src[si];
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int bi = bi0 + ty + 8 * k;
-        const long long di = mode == 2 ? (((long long)rr * s + ss) * b + bi) * a + ai0 + tx
-                                       : (((long long)(grp * b + bi) * r + rr) * s + ss) * ag + ai0 + tx;
-        dst[di] = from_f<TD>(tile[tx][ty + 8 * k]);
-      }
-      __syncthreads();
-    }
-    return;
-  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long si;
     if (mode == 0) {
