@@ -299,11 +299,12 @@ int xv2_save_probs(const float* logits, int32_t n, int64_t hw, int32_t ncls, flo
  * ---------------------------------------------------------------------------------------------------------- */
 /* xv2_splat_bn_gap with the bn0 finalize step folded in (one launch fewer per bottleneck): the coefficients come straight from
  * the fp64 (sum, sum of squares) `stats` of the radix conv's epilogue; block (0,0) writes coef = [4][2c] mean | invstd | scale |
- * shift for the later kernels and updates the running statistics exactly as xv2_bn_finalize does.  gap_is_zero != 0: the caller
- * hands in zero-filled memory (the step's scratch arena) and no memset node is issued. */
+ * shift for the later kernels and updates the running statistics exactly as xv2_bn_finalize does.  The pooled sums are accumulated
+ * in fp64 in `gap_acc` ([n][c], ZERO-FILLED by the caller: the step's scratch arena) and converted to gap = fp32(sum / hw) by a
+ * second, tiny launch: the result does not depend on the order in which the blocks arrive (run-to-run reproducible forward). */
 int xv2_splat_bn_gap_fin(const void* z, const double* stats, int64_t count, const float* gamma, const float* beta,
                          float* running_mean, float* running_var, float momentum, float eps, float* coef, float* gap,
-                         int32_t gap_is_zero, int32_t n, int64_t hw, int32_t c, void* stream);
+                         double* gap_acc, int32_t n, int64_t hw, int32_t c, void* stream);
 /* xv2_splat_fc_bwd for the bn0-fused path with the two tiny neighbours folded in (two launches fewer per bottleneck): datt is
  * derived from `part` (as xv2_splat_bn_bwd_datt) inside the first FC kernel, and the bn0 reductions `red` (as
  * xv2_splat_bn_bwd_red) are finished by the last one, which has just produced dgap.  accumulate != 0: dw2 / db2 / dw1 / db1 /

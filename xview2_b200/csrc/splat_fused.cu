@@ -111,7 +111,8 @@ __device__ __forceinline__ void splat_finalize_channel(const SplatFin& f, int c2
 
 __global__ void __launch_bounds__(256) splat_bn_gap_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, float* __restrict__ gap,
-                                                           long long hw, int c, float inv_hw, SplatMap m, SplatFin fin) {
+                                                           long long hw, int c, float inv_hw, SplatMap m, SplatFin fin,
+                                                           double* __restrict__ gap_acc) {
   __shared__ float sm[256][8];
   const int cvi = threadIdx.x % m.cvt, lane = threadIdx.x / m.cvt;
   const int ch0 = cvi * 8, nb = blockIdx.y;
@@ -169,8 +170,17 @@ __global__ void __launch_bounds__(256) splat_bn_gap_kernel(const __nv_bfloat16* 
   }
   block_reduce_vec8(sm, acc, m.cvt, [&](int cv, int i, float t) {
     const int ch = cv * 8 + i;
-    atomicAdd(&gap[(long long)nb * c + (ch >= c ? ch - c : ch)], t * inv_hw);  // both radix halves add into one gap channel
+    const long long gi = (long long)nb * c + (ch >= c ? ch - c : ch);  // both radix halves add into one gap channel
+    // fp64 accumulation: the order of the per-block contributions no longer shows in the fp32 result (an fp32 atomic sum made
+    // two identical runs differ by rounding flips that the BatchNorm over the n pooled vectors then amplified)
+    if (gap_acc != nullptr) atomicAdd(&gap_acc[gi], (double)t);
+    else atomicAdd(&gap[gi], t * inv_hw);
   });
+}
+
+__global__ void splat_gap_finish_kernel(const double* __restrict__ gap_acc, float* __restrict__ gap, int total, double inv_hw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) gap[i] = (float)(gap_acc[i] * inv_hw);
 }
 
 // ---- forward 2: combine (a thread owns BOTH radix halves of its 8 channels) ---------------------------------------
@@ -408,18 +418,17 @@ extern "C" int xv2_splat_bn_gap(const void* z, const float* scale, const float* 
   SplatFin fin;
   memset(&fin, 0, sizeof(fin));
   splat_bn_gap_kernel<<<splat_grid(n, hw, m.lanes, 16), 256, 0, st>>>((const __nv_bfloat16*)z, scale, shift, gap, hw, c,
-                                                                     1.0f / (float)hw, m, fin);
+                                                                     1.0f / (float)hw, m, fin, nullptr);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }
 
 extern "C" int xv2_splat_bn_gap_fin(const void* z, const double* stats, int64_t count, const float* gamma, const float* beta,
                                     float* running_mean, float* running_var, float momentum, float eps, float* coef, float* gap,
-                                    int32_t gap_is_zero, int32_t n, int64_t hw, int32_t c, void* stream) {
-  XV2_REQUIRE(z && stats && coef && gap && count > 0, "splat_bn_gap_fin: bad argument");
+                                    double* gap_acc, int32_t n, int64_t hw, int32_t c, void* stream) {
+  XV2_REQUIRE(z && stats && coef && gap && gap_acc && count > 0, "splat_bn_gap_fin: bad argument");
   XV2_SPLAT_SHAPE("splat_bn_gap_fin", 2 * c / 8)
   cudaStream_t st = as_stream(stream);
-  if (!gap_is_zero) cudaMemsetAsync(gap, 0, sizeof(float) * (size_t)n * c, st);
   SplatFin fin;
   fin.stats = stats;
   fin.gamma = gamma;
@@ -431,7 +440,8 @@ extern "C" int xv2_splat_bn_gap_fin(const void* z, const double* stats, int64_t 
   fin.eps = eps;
   fin.count = count;
   splat_bn_gap_kernel<<<splat_grid(n, hw, m.lanes, 16), 256, 0, st>>>((const __nv_bfloat16*)z, nullptr, nullptr, gap, hw, c,
-                                                                     1.0f / (float)hw, m, fin);
+                                                                     1.0f / (float)hw, m, fin, gap_acc);
+  splat_gap_finish_kernel<<<(n * c + 255) / 256, 256, 0, st>>>(gap_acc, gap, n * c, 1.0 / (double)hw);
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }

@@ -62,7 +62,7 @@ _SIGNATURES = {
     "xv2_rsoftmax_bwd": [P, P, P, I32, I32, P],
     "xv2_splat_fc_fwd": [P, P, P, P, P, P, P, F, F, I32, P, P, P, P, P, P, I32, I32, I32, P],
     "xv2_splat_fc_bwd": [P, P, P, P, P, P, P, P, P, I32, P, P, P, P, P, P, P, P, P, I32, I32, I32, P],
-    "xv2_splat_bn_gap_fin": [P, P, I64, P, P, P, P, F, F, P, P, I32, I32, I64, I32, P],
+    "xv2_splat_bn_gap_fin": [P, P, I64, P, P, P, P, F, F, P, P, P, I32, I64, I32, P],
     "xv2_splat_fc_bwd_fused": [P, P, P, P, P, P, I64, P, P, P, P, P, P, P, I32, P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P],
     "xv2_splat_combine": [P, P, P, I32, I64, I32, I32, P],
     "xv2_splat_bwd_att": [P, P, P, I32, I64, I32, I32, P],

@@ -1041,11 +1041,12 @@ class _BnSplitAttention(torch.autograd.Function):
         inter = w1.shape[0]
         dev = z.device
         coef0 = torch.empty(4, c2, dtype=torch.float32, device=dev)  # mean, invstd, scale, shift of bn0
-        gap = zeros_scratch((n, c), torch.float32, dev)  # zero-filled with the step's arena: no memset node of its own
+        gap = torch.empty((n, c), dtype=torch.float32, device=dev)
+        gap_acc = zeros_scratch((n, c), torch.float64, dev)  # fp64 accumulator, zero-filled with the step's arena (no memset node)
         lib.note_work(0.0, 2.0 * n * hw * c2, f"splat bn+gap n{n} {h}x{w} c{c}")
         # bn0's finalize step (coefficients, running statistics) is folded into the GAP kernel's prologue
         call("xv2_splat_bn_gap_fin", ptr(z), ptr(stats), n * hw, ptr(g0), ptr(b0), ptr(rm0), ptr(rv0), float(mom0), float(eps0),
-             ptr(coef0), ptr(gap), 1, n, hw, c)
+             ptr(coef0), ptr(gap), ptr(gap_acc), n, hw, c)
         w1m, w2m = w1.reshape(inter, c).contiguous(), w2.reshape(c2, inter).contiguous()
         z1 = torch.empty((n, inter), dtype=torch.float32, device=dev)
         a1 = torch.empty_like(z1)
