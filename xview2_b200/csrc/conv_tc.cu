@@ -244,22 +244,29 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       for (int sb = half; sb < nblocks; sb += 2) {
         const uint32_t sbuf = sbuf0 + obuf * 16384;
         const uint32_t row_addr = sbuf + m * rowb;
+        // Both 32-column TMEM loads of the block are issued BEFORE the buffer hand-over (bulk wait + barrier) and waited for once:
+        // with N = 256 and a one-k-block main loop (1x1 convs c -> 4c, transposed convs) the tile time IS the epilogue
+        // (ncu: 92 us at 9 % tensor pipe for c64 -> 256 @256^2), so TMEM latency must hide behind the barrier, not add to it.
+        uint32_t v[64];
+        tmem_ld_32x32(trow + sb * p.store_c, v);
+        if (p.store_c == 64) tmem_ld_32x32(trow + sb * p.store_c + 32, v + 32);
         if (issuer) {  // the TMA store that last read THIS buffer has finished reading it
           if (p.out_bufs == 2) bulk_wait_read1();
           else bulk_wait_read0();
         }
         named_bar_sync(1 + half, 128);
-        for (int part = 0; part < p.store_c; part += 32) {
+        tmem_ld_wait();
+#pragma unroll
+        for (int pi = 0; pi < 2; ++pi) {
+          const int part = pi * 32;
+          if (part >= p.store_c) continue;
           const int col = sb * p.store_c + part;
-          uint32_t v[32];
-          tmem_ld_32x32(trow + col, v);
-          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint32_t w4[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float a = __uint_as_float(v[j + 2 * i]), b = __uint_as_float(v[j + 2 * i + 1]);
+              float a = __uint_as_float(v[part + j + 2 * i]), b = __uint_as_float(v[part + j + 2 * i + 1]);
               if (p.bias) {
                 a += p.bias[co0 + col + j + 2 * i];
                 b += p.bias[co0 + col + j + 2 * i + 1];
