@@ -516,3 +516,76 @@ def test_batched_repack_equals_single_pack():
     for (shape, mode, dtype, groups), w, ref in zip(cases, weights, single):
         got = ops.pack_weight(w, mode, dtype, groups)  # valid stamp: returned as the batched launch left it
         assert torch.equal(got, ref), (shape, mode, dtype, groups)
+
+
+def test_folded_split_attention_entries_equal_their_unfolded_pieces():
+    """The per-bottleneck launches folded away this round, checked at the C ABI: xv2_splat_bn_gap_fin == xv2_bn_finalize +
+    xv2_splat_bn_gap (coefficients / running statistics bit-exact, pooled vector to fp32 rounding: the folded entry accumulates
+    in fp64), xv2_splat_fc_bwd_fused == xv2_splat_bn_bwd_datt + xv2_splat_fc_bwd + xv2_splat_bn_bwd_red (bit-exact), and its
+    accumulate mode adds onto what the destinations already hold."""
+    from xview2_b200 import lib
+    from xview2_b200.lib import BF16, call, ptr
+    lib.init(torch.cuda.current_device())
+    n, c, hw, inter = 4, 64, 32 * 32, 32
+    c2 = 2 * c
+    f32 = dict(dtype=torch.float32, device="cuda")
+    z = rnd(n, hw, c2, dtype=torch.bfloat16, seed=1)
+    dout = rnd(n, hw, c, dtype=torch.bfloat16, seed=2)
+    g0, b0 = rnd(c2, seed=3) * 0.2 + 1, rnd(c2, seed=4) * 0.2
+    stats = torch.zeros(2 * c2, dtype=torch.float64, device="cuda")
+    call("xv2_bn_stats", ptr(z), n * hw, c2, BF16, ptr(stats))
+    # ---- forward: finalize + gap vs the folded entry
+    rm_a, rv_a = torch.zeros(c2, **f32), torch.ones(c2, **f32)
+    rm_b, rv_b = rm_a.clone(), rv_a.clone()
+    coef_a, coef_b = torch.empty(4, c2, **f32), torch.empty(4, c2, **f32)
+    call("xv2_bn_finalize", ptr(stats), n * hw, c2, ptr(g0), ptr(b0), ptr(rm_a), ptr(rv_a), 0.1, 1e-5, ptr(coef_a[0]), ptr(coef_a[1]),
+         ptr(coef_a[2]), ptr(coef_a[3]))
+    gap_a = torch.empty(n, c, **f32)
+    call("xv2_splat_bn_gap", ptr(z), ptr(coef_a[2]), ptr(coef_a[3]), ptr(gap_a), n, hw, c)
+    gap_b, gap_acc = torch.empty(n, c, **f32), torch.zeros(n, c, dtype=torch.float64, device="cuda")
+    call("xv2_splat_bn_gap_fin", ptr(z), ptr(stats), n * hw, ptr(g0), ptr(b0), ptr(rm_b), ptr(rv_b), 0.1, 1e-5, ptr(coef_b), ptr(gap_b),
+         ptr(gap_acc), n, hw, c)
+    assert torch.equal(coef_a, coef_b) and torch.equal(rm_a, rm_b) and torch.equal(rv_a, rv_b)
+    assert rel(gap_b, gap_a) < 1e-5
+    # ---- the FC chain forward (shared by both paths) for att / a1 / z1 / coef
+    w1, b1 = rnd(inter, c, seed=5) * 0.1, rnd(inter, seed=6) * 0.1
+    w2, b2 = rnd(c2, inter, seed=7) * 0.1, rnd(c2, seed=8) * 0.1
+    g1, be1 = rnd(inter, seed=9) * 0.2 + 1, rnd(inter, seed=10) * 0.2
+    rm1, rv1 = torch.zeros(inter, **f32), torch.ones(inter, **f32)
+    z1, a1, coef1, att = torch.empty(n, inter, **f32), torch.empty(n, inter, **f32), torch.empty(4, inter, **f32), torch.empty(n, c2, **f32)
+    call("xv2_splat_fc_fwd", ptr(gap_b), ptr(w1), ptr(b1), ptr(g1), ptr(be1), ptr(rm1), ptr(rv1), 0.1, 1e-5, 1, ptr(w2), ptr(b2), ptr(z1),
+         ptr(a1), ptr(coef1), ptr(att), n, c, inter)
+    part = torch.zeros(4, n, c2, dtype=torch.float64, device="cuda")
+    call("xv2_splat_bn_bwd_partials", ptr(z), ptr(dout), ptr(coef_a[2]), ptr(coef_a[3]), ptr(part), n, hw, c)
+    w2t, w1t = w2.t().contiguous(), w1.t().contiguous()
+
+    def outs(fill=0.0):
+        o = {"dz2": torch.empty(n, c2, **f32), "dz1": torch.empty(n, inter, **f32), "dw2": torch.full((c2, inter), fill, **f32),
+             "db2": torch.full((c2,), fill, **f32), "dw1": torch.full((inter, c), fill, **f32), "db1": torch.full((inter,), fill, **f32),
+             "dgamma": torch.full((inter,), fill, **f32), "dbeta": torch.full((inter,), fill, **f32), "dgap": torch.empty(n, c, **f32),
+             "red": torch.empty(2 * c2, dtype=torch.float64, device="cuda")}
+        return o
+
+    # ---- backward: datt + fc_bwd + red vs the folded entry
+    a = outs()
+    datt = torch.empty(n, c2, **f32)
+    call("xv2_splat_bn_bwd_datt", ptr(part), ptr(coef_a[2]), ptr(coef_a[3]), ptr(datt), n, c)
+    call("xv2_splat_fc_bwd", ptr(att), ptr(datt), ptr(a1), ptr(z1), ptr(coef1), ptr(g1), ptr(gap_b), ptr(w2t), ptr(w1t), 1, ptr(a["dz2"]),
+         ptr(a["dz1"]), ptr(a["dw2"]), ptr(a["db2"]), ptr(a["dw1"]), ptr(a["db1"]), ptr(a["dgamma"]), ptr(a["dbeta"]), ptr(a["dgap"]), n, c,
+         inter)
+    call("xv2_splat_bn_bwd_red", ptr(part), ptr(att), ptr(a["dgap"]), ptr(coef_a[0]), ptr(coef_a[1]), ptr(a["red"]), n, hw, c)
+
+    def fused(o, accumulate):
+        call("xv2_splat_fc_bwd_fused", ptr(att), ptr(part), ptr(coef_a[2]), ptr(coef_a[3]), ptr(coef_a[0]), ptr(coef_a[1]), hw, ptr(a1),
+             ptr(z1), ptr(coef1), ptr(g1), ptr(gap_b), ptr(w2t), ptr(w1t), 1, ptr(o["dz2"]), ptr(o["dz1"]), ptr(o["dw2"]), ptr(o["db2"]),
+             ptr(o["dw1"]), ptr(o["db1"]), ptr(o["dgamma"]), ptr(o["dbeta"]), ptr(o["dgap"]), ptr(o["red"]), accumulate, n, c, inter)
+
+    b = outs(7.0)  # garbage in the destinations: accumulate = 0 must overwrite it
+    fused(b, 0)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    acc = outs(0.5)
+    fused(acc, 1)
+    for k in ("dw2", "db2", "dw1", "db1", "dgamma", "dbeta"):
+        assert torch.equal(acc[k], a[k] + 0.5), k
+    assert torch.equal(acc["dgap"], a["dgap"]) and torch.equal(acc["red"], a["red"])

@@ -25,7 +25,6 @@ a = ap.parse_args()
 a.gpus = 1
 torch.cuda.set_device(0)
 lib.init(0)
-ops.enable_wgrad_side_stream(True)
 ns = bench.config_namespace(a)
 torch.manual_seed(1)
 model = Model(ns).cuda().train()

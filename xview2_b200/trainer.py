@@ -145,8 +145,7 @@ class Trainer:
         flat.broadcast_params(0)
         if self.world_size > 1:
             flat.enable_bucketed_allreduce(model)  # DDP-style overlap of the gradient all-reduce with backward (main.py:106-107)
-        from . import ops
-        ops.enable_wgrad_side_stream(True)  # step()/all_reduce_grads()/zero_grad() below are the sync points
+        from . import ops  # weight gradients stay on the compute stream (a side stream measured neutral: DESIGN.md section 4)
         self.scheduler = scheduler
         if resume is not None and resume.get("optimizer"):
             optimizer.load_state_dict(resume["optimizer"])
