@@ -265,6 +265,52 @@ __device__ __forceinline__ void pack_job(const xv2_pack_job& j) {
   const int a = j.a, r = j.r, s = j.s, b = j.b, mode = j.mode;
   const long long total = (long long)a * r * s * b;
   const int ag = a / j.groups;
+  if (mode != 0 && ag % 16 == 0 && b % 32 == 0) {
+    // Modes 1 / 2 transpose the (out-channel, in-channel) pair of every tap.  Register transpose, no shared memory: a warp reads
+    // 16 source rows (ai) as 16 coalesced 128-byte loads -- lane = bi -- and every lane then owns 16 CONSECUTIVE destination
+    // elements (ai0 .. ai0+15 of its row bi), written as full 32-byte (bf16) / 64-byte (fp32) segments.  The element-wise loop
+    // below reads with a stride of r*s*b floats: one 32-byte sector per 4-byte element, which made the re-pack L2-bound
+    // (3.65 ms per step at BASELINE config 4, 386 M parameters).
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int ta = ag / 16, tb = b / 32;
+    const long long nitems = (long long)j.groups * r * s * ta * tb;
+    for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nitems; it += nwarps) {
+      long long q = it;
+      const int bt = (int)(q % tb); q /= tb;
+      const int at = (int)(q % ta); q /= ta;
+      const int ss = (int)(q % s); q /= s;
+      const int rr = (int)(q % r);
+      const int grp = (int)(q / r);
+      const int bi = bt * 32 + lane, ai0 = at * 16;
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int ai = ai0 + k;
+        const long long si = mode == 2 ? (((long long)ai * r + rr) * s + ss) * b + bi
+                                       : (((long long)(grp * ag + ai) * r + (r - 1 - rr)) * s + (s - 1 - ss)) * b + bi;
+        v[k] = src[si];
+      }
+      const long long di = mode == 2 ? (((long long)rr * s + ss) * b + bi) * a + ai0
+                                     : (((long long)(grp * b + bi) * r + rr) * s + ss) * ag + ai0;
+      if constexpr (sizeof(TD) == 2) {
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+          w[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint4* o = reinterpret_cast<uint4*>(dst + di);
+        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      } else {
+        float4* o = reinterpret_cast<float4*>(dst + di);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      }
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long si;
     if (mode == 0) {
@@ -401,7 +447,7 @@ extern "C" int xv2_pack_weight(const float* src, void* dst, int32_t a, int32_t r
 
 extern "C" int xv2_pack_weights_batched(const xv2_pack_job* jobs, int32_t njobs, void* stream) {
   XV2_REQUIRE(jobs != nullptr && njobs > 0 && njobs <= 65535, "pack_weights_batched: bad job table");
-  pack_weights_batched_kernel<<<dim3(192, njobs), 256, 0, as_stream(stream)>>>(jobs);
+  pack_weights_batched_kernel<<<dim3(192, njobs), 256, 0, as_stream(stream)>>>(jobs);  // measured: 592 CTAs per job is slower (empty CTAs of the ~340 small jobs)
   XV2_LAUNCH_CHECK();
   return XV2_OK;
 }
