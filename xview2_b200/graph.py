@@ -74,6 +74,7 @@ class GraphedTrainStep:
         with ops.defer_nbt():  # the 81 num_batches_tracked += 1 launches of the forward become one multi-tensor add
             loss = self.model.training_step(self.static, 0)
         loss.backward()
+        ops.check_pending_addends()  # every gradient part parked by ops.fork has been collected by its BatchNorm backward
         return loss.detach()
 
     def _finish(self):

@@ -189,7 +189,6 @@ class _OnSide:
 def sync_side_streams():
     """The current stream waits for every weight gradient issued on a side stream (called before the gradient all-reduce /
     optimizer step / anything that reads .grad)."""
-    check_pending_addends()
     cur = torch.cuda.current_stream() if torch.cuda.is_available() else None
     for st in list(_side_dirty):
         cur.wait_stream(st)

@@ -139,6 +139,7 @@ class FlatParams:
         """all-reduce(SUM) of the flat gradient buffer over the data-parallel ranks; returns the world size (the 1/N
         average is applied by the optimizer through its ``grad_scale``)."""
         ops.sync_side_streams()  # weight gradients issued on the side stream have landed in the flat buffer
+        ops.check_pending_addends()  # backward is over: a gradient part still parked by ops.fork would be a silently wrong step
         dist = torch.distributed
         if not (dist.is_available() and dist.is_initialized()):
             return 1
