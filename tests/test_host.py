@@ -578,3 +578,19 @@ def test_deferred_num_batches_tracked_counts_every_visit():
             ops._bump_nbt(bns[2])
             raise ValueError("forward failed")
     assert int(bns[2].num_batches_tracked) == 1                        # a failed forward applies nothing
+
+
+def test_every_abi_declaration_sits_under_a_reference_citation():
+    """include/xv2.h: each entry point is declared under a comment (its own or its section's) that cites the reference call site
+    it replaces as file.py:line -- the drop-in boundary is documented where it is declared."""
+    lines = open(os.path.join(ROOT, "include", "xv2.h")).read().splitlines()
+    cite = re.compile(r"[a-z_0-9]+\.py:\d+")
+    housekeeping = {"xv2_last_error", "xv2_version", "xv2_init"}
+    seen = 0
+    for i, line in enumerate(lines):
+        m = re.match(r"(?:int|const char\*) (xv2_[a-z0-9_]+)\s*\(", line)
+        if not m or m.group(1) in housekeeping:
+            continue
+        seen += 1
+        assert cite.search("\n".join(lines[max(0, i - 60):i])), f"{m.group(1)}: no reference file:line above its declaration"
+    assert seen >= 70
